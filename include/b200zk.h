@@ -1,0 +1,158 @@
+/* libb200zk -- C ABI of the B200-native Groth16 (BLS12-381) proving backend.
+ *
+ * This is the drop-in boundary for the prove path of ArielElb/zkSnark-FinalProject.
+ * The reference has no FFI of its own: its handlers call the arkworks trait
+ * surface directly, so each entry point below names the arkworks call (and the
+ * reference call site) it replaces.  A Rust shim packs arkworks
+ * values into these plain buffers; nothing here mentions torch or C++ types.
+ *
+ * Data layouts (identical to arkworks' in-memory forms, so the shim copies limbs):
+ *   Fr element   : 4 x uint64 little-endian limbs, Montgomery form, R = 2^256
+ *                  (ark_ff::Fp<MontBackend<FrConfig,4>,4>.0.0)
+ *   Fr "bigint"  : 4 x uint64 little-endian limbs, canonical (into_bigint())
+ *   Fq element   : 6 x uint64 limbs, Montgomery form, R = 2^384
+ *   G1 affine    : x, y            -> 12 x uint64 (96 B); infinity flagged separately
+ *   G2 affine    : x.c0, x.c1, y.c0, y.c1 -> 24 x uint64 (192 B)
+ *   infinity map : 1 bit per point, bit i of byte i/8 (LSB first); NULL = no
+ *                  point is the identity
+ *   projective   : X, Y, Z Jacobian as arkworks' Projective {x, y, z}; Z = 0 is
+ *                  the identity
+ *
+ * Threading: a b2z_ctx serialises the calls made on it (internal mutex); use one
+ * ctx per host thread (actix worker, /root/reference/src/main.rs:37) for
+ * concurrency.  Errors never unwind across the boundary: every call returns a
+ * b2z_status and b2z_last_error() describes the most recent failure on that ctx.
+ */
+#ifndef B200ZK_H_
+#define B200ZK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define B2Z_API __attribute__((visibility("default")))
+#else
+#define B2Z_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t b2z_status;
+enum {
+  B2Z_OK = 0,
+  B2Z_EINVAL = 1,  /* bad argument (NULL buffer, inconsistent sizes)                */
+  B2Z_ESIZE = 2,   /* domain too large: log_n > 32 (ark-poly returns None ->
+                      SynthesisError::PolynomialDegreeTooLarge)                     */
+  B2Z_ECUDA = 3,   /* CUDA runtime failure, incl. "no CUDA device": there is no
+                      CPU fallback                                                  */
+  B2Z_ENOMEM = 4   /* device or pinned-host allocation failed                       */
+};
+
+typedef struct b2z_ctx b2z_ctx;
+typedef struct b2z_pk b2z_pk;
+
+/* One context per (host thread, device).  device_id is a CUDA ordinal. */
+B2Z_API b2z_status b2z_ctx_create(int device_id, b2z_ctx** out);
+B2Z_API void b2z_ctx_destroy(b2z_ctx* ctx);
+B2Z_API const char* b2z_last_error(const b2z_ctx* ctx);
+
+/* ---- ark_poly::Radix2EvaluationDomain<Fr> -------------------------------------
+ * Replaces fft_in_place / ifft_in_place on `domain` and on
+ * `domain.get_coset(g)` (used by LibsnarkReduction::witness_map_from_matrices,
+ * reached from Groth16::prove at src/arkworks/backend/matrix_proof.rs:139).
+ * data: n = 2^log_n Fr elements (host memory), transformed in place, natural
+ * order in and out.  coset_gen: NULL for the base domain, else the coset offset
+ * g as an Fr element; forward evaluates at g*w^k, inverse undoes exactly that. */
+B2Z_API b2z_status b2z_ntt_fr(b2z_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse,
+                      const uint64_t coset_gen[4]);
+
+/* ---- ark_groth16::r1cs_to_qap::LibsnarkReduction::witness_map_from_matrices ----
+ * after its sparse row evaluations: a, b, c are the length-n (n = 2^log_n)
+ * evaluation vectors (a[num_constraints + j] = z[j] already placed, zero padded);
+ * h_out receives the n coefficients of (A*B - C)/Z_H, natural order.             */
+B2Z_API b2z_status b2z_witness_map(b2z_ctx* ctx, const uint64_t* a, const uint64_t* b,
+                           const uint64_t* c, uint32_t log_n, uint64_t* h_out);
+
+/* ---- ark_ec::VariableBaseMSM::msm_bigint --------------------------------------
+ * for G1Projective / G2Projective (called five times per proof by
+ * create_proof_with_assignment).  bases: n affine points; scalars: n canonical
+ * bigints; out: one Jacobian point (18 / 36 limbs), canonical Montgomery limbs.   */
+B2Z_API b2z_status b2z_msm_g1(b2z_ctx* ctx, const uint64_t* bases, const uint8_t* inf_bitmap,
+                      const uint64_t* scalars, uint64_t n, uint64_t out_xyz[18]);
+B2Z_API b2z_status b2z_msm_g2(b2z_ctx* ctx, const uint64_t* bases, const uint8_t* inf_bitmap,
+                      const uint64_t* scalars, uint64_t n, uint64_t out_xyz[36]);
+
+/* ---- ark_groth16::ProvingKey<Bls12_381> ---------------------------------------
+ * Uploaded once per circuit (the reference re-runs setup per request,
+ * matrix_proof.rs:129; a shim may cache by circuit shape), then proved against
+ * many times.  All arrays are copied; the caller keeps ownership.               */
+typedef struct b2z_pk_desc {
+  uint64_t num_variables;    /* m: instance (incl. the constant 1) + witness              */
+  uint64_t num_instance;     /* l                                                          */
+  uint32_t log_domain;       /* n = 2^log_domain                                           */
+  const uint64_t* a_query;   const uint8_t* a_inf;      /* m  G1 */
+  const uint64_t* b_g1_query; const uint8_t* b_g1_inf;  /* m  G1 */
+  const uint64_t* b_g2_query; const uint8_t* b_g2_inf;  /* m  G2 */
+  const uint64_t* h_query;   const uint8_t* h_inf;      /* n - 1  G1 */
+  const uint64_t* l_query;   const uint8_t* l_inf;      /* m - l  G1 */
+  const uint64_t* alpha_g1;  /* vk.alpha_g1  (12 limbs) */
+  const uint64_t* beta_g1;   /* pk.beta_g1               */
+  const uint64_t* delta_g1;  /* pk.delta_g1              */
+  const uint64_t* beta_g2;   /* vk.beta_g2   (24 limbs) */
+  const uint64_t* delta_g2;  /* vk.delta_g2              */
+} b2z_pk_desc;
+
+B2Z_API b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* desc, b2z_pk** out);
+B2Z_API void b2z_pk_free(b2z_ctx* ctx, b2z_pk* pk);
+
+/* ---- ark_groth16::Groth16::<Bls12_381>::create_proof_with_reduction ------------
+ * minus circuit synthesis (which stays in Rust): the call at
+ * fibbonaci_handler.rs:110, matrix_proof.rs:139-140, prime_snark.rs:119.
+ *   a/b/c_evals : as for b2z_witness_map (n = 2^pk.log_domain elements each)
+ *   z           : full assignment, m Fr elements (Montgomery), z[0] = 1
+ *   r, s        : the prover's two Fr::rand draws (Montgomery), made by the host
+ *   proof_out   : Proof::serialize_compressed bytes, A(48) | B(96) | C(48)
+ *                 (what encode_proof base64-encodes, matrix_proof_of_work/io.rs:48) */
+B2Z_API b2z_status b2z_groth16_prove(b2z_ctx* ctx, const b2z_pk* pk, const uint64_t* a_evals,
+                             const uint64_t* b_evals, const uint64_t* c_evals,
+                             const uint64_t* z, const uint64_t r[4], const uint64_t s[4],
+                             uint8_t proof_out[192]);
+
+/* Same computation on inputs already resident in device memory (device pointers
+ * on ctx's device; a/b/c are clobbered).  Used to separate kernel time from
+ * PCIe time in benchmarks; the proof bytes still land in host memory.            */
+B2Z_API b2z_status b2z_groth16_prove_device(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_a,
+                                    uint64_t* d_b, uint64_t* d_c, const uint64_t* d_z,
+                                    const uint64_t r[4], const uint64_t s[4],
+                                    uint8_t proof_out[192]);
+
+/* ---- ark_ec::scalar_mul::fixed_base::FixedBase::msm ------------------------------
+ * on the standard generators: out[i] = scalars[i] * G.  ark-groth16's setup builds
+ * every query array this way (Groth16::setup, matrix_proof.rs:129); the benchmarks
+ * use it to make synthetic bases.  scalars: canonical bigints; out: affine points
+ * (12 / 24 limbs each); out_inf: identity bitmap, (n + 7) / 8 bytes.                */
+B2Z_API b2z_status b2z_fixed_base_mul_g1(b2z_ctx* ctx, const uint64_t* scalars, uint64_t n,
+                                         uint64_t* out_points, uint8_t* out_inf);
+B2Z_API b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t n,
+                                         uint64_t* out_points, uint8_t* out_inf);
+
+/* ---- host-side self checks (no GPU needed) -------------------------------------------
+ * The limb algorithms of the device code are written against a carry-flag
+ * abstraction that also runs on the host; these entry points let the CPU-only test
+ * suite check them against the oracle.  op: 0 mul, 1 add, 2 sub, 3 canonical form,
+ * 4 inverse.  field: 0 = Fr (8 x u32), 1 = Fq (12 x u32); operands lazy (< 2p).      */
+B2Z_API int b2z_host_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* sum of n affine points (Montgomery limbs, 24 / 48 u32 each; neg[i] != 0 negates) with the
+ * device's XYZZ mixed-addition code; out = affine sum, returns 1 if the sum is the identity. */
+B2Z_API int b2z_host_point_sum(int group /*1|2*/, const uint32_t* points, const uint8_t* neg, uint32_t n,
+                               uint32_t* out_affine);
+/* signed digits of a canonical scalar as the MSM kernels see them; returns the window count */
+B2Z_API uint32_t b2z_host_msm_digits(const uint32_t scalar[8], uint32_t c, int32_t* digits /* >= 64 */);
+B2Z_API uint32_t b2z_host_msm_window_bits(uint64_t n, int precomputed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H_ */

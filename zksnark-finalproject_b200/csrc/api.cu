@@ -1,0 +1,105 @@
+// extern "C" entry points of libb200zk (see include/b200zk.h for the contract).
+// Every entry point catches StatusError so nothing unwinds across the boundary.
+#include <cstring>
+
+#include "api_glue.hpp"
+#include "msm.hpp"
+
+using namespace b2z;
+
+extern "C" {
+
+b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
+  if (out == nullptr) return B2Z_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return B2Z_ECUDA;   // no CPU fallback
+  if (device_id < 0 || device_id >= count) return B2Z_EINVAL;
+  b2z_ctx* ctx = new (std::nothrow) b2z_ctx();
+  if (ctx == nullptr) return B2Z_ENOMEM;
+  ctx->impl.device = device_id;
+  try {
+    B2Z_CUDA(cudaSetDevice(device_id));
+    B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->impl.stream, cudaStreamNonBlocking));
+    for (auto& s : ctx->impl.aux) B2Z_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  } catch (const StatusError& e) {
+    delete ctx;
+    return e.code;
+  }
+  *out = ctx;
+  return B2Z_OK;
+}
+
+void b2z_ctx_destroy(b2z_ctx* ctx) {
+  if (ctx == nullptr) return;
+  cudaSetDevice(ctx->impl.device);
+  cudaDeviceSynchronize();
+  ctx->impl.domains.clear();
+  msm_release_scratch(&ctx->impl);
+  if (ctx->impl.stream) cudaStreamDestroy(ctx->impl.stream);
+  for (auto& s : ctx->impl.aux)
+    if (s) cudaStreamDestroy(s);
+  delete ctx;
+}
+
+const char* b2z_last_error(const b2z_ctx* ctx) { return ctx ? ctx->impl.last_error.c_str() : "null context"; }
+
+b2z_status b2z_ntt_fr(b2z_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse, const uint64_t coset_gen[4]) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(data != nullptr, B2Z_EINVAL, "b2z_ntt_fr: data is NULL");
+    B2Z_REQUIRE(log_n <= 32, B2Z_ESIZE, "b2z_ntt_fr: domain larger than 2^32 (PolynomialDegreeTooLarge)");
+    B2Z_REQUIRE(log_n <= 28, B2Z_ENOMEM, "b2z_ntt_fr: domain does not fit this build's single-GPU plan");
+    const size_t n = (size_t)1 << log_n;
+    cudaStream_t st = c.stream;
+    DevBuf<FrEl> d(n);
+    B2Z_CUDA(cudaMemcpyAsync(d.p, data, n * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    DevBuf<FrEl> pw_lo, pw_hi;
+    const bool coset = coset_gen != nullptr;
+    if (coset) {
+      // g^i (forward) or g^-i (inverse) as lo[i & 1023] * hi[i >> 10]
+      FrEl g;
+      std::memcpy(g.l, coset_gen, sizeof(g.l));
+      g = Fr::reduce(g);
+      if (inverse) g = Fr::reduce(Fr::inv(g));
+      FrEl g1024 = g;
+      for (int i = 0; i < 10; i++) g1024 = Fr::sqr(g1024);
+      g1024 = Fr::reduce(g1024);
+      const uint32_t nhi = (uint32_t)((n + 1023) >> 10);
+      pw_lo.alloc(1024);
+      pw_hi.alloc(nhi);
+      fr_pow_table(pw_lo.p, g, 1024, st);
+      fr_pow_table(pw_hi.p, g1024, nhi, st);
+    }
+    if (!inverse) {
+      if (coset) ntt_scale_powers(d.p, log_n, pw_lo.p, pw_hi.p, st);
+      ntt_dif(ntt_twiddles(&c, log_n, TW_FWD, st), d.p, log_n, st);
+      ntt_bitrev(d.p, log_n, nullptr, nullptr, nullptr, st);
+    } else {
+      ntt_dif(ntt_twiddles(&c, log_n, TW_INV, st), d.p, log_n, st);
+      const NttDomain& dom = ntt_domain(&c, log_n);
+      ntt_bitrev(d.p, log_n, &dom.n_inv, coset ? pw_lo.p : nullptr, coset ? pw_hi.p : nullptr, st);
+    }
+    B2Z_CUDA(cudaMemcpyAsync(data, d.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+b2z_status b2z_witness_map(b2z_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* cc, uint32_t log_n,
+                           uint64_t* h_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(a && b && cc && h_out, B2Z_EINVAL, "b2z_witness_map: NULL buffer");
+    B2Z_REQUIRE(log_n <= 32, B2Z_ESIZE, "b2z_witness_map: domain larger than 2^32 (PolynomialDegreeTooLarge)");
+    B2Z_REQUIRE(log_n <= 28, B2Z_ENOMEM, "b2z_witness_map: domain does not fit this build's single-GPU plan");
+    const size_t n = (size_t)1 << log_n;
+    cudaStream_t st = c.stream;
+    DevBuf<FrEl> da(n), db(n), dc(n);
+    B2Z_CUDA(cudaMemcpyAsync(da.p, a, n * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    B2Z_CUDA(cudaMemcpyAsync(db.p, b, n * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    B2Z_CUDA(cudaMemcpyAsync(dc.p, cc, n * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    witness_map_device(&c, da.p, db.p, dc.p, log_n, /*natural_out=*/true, st);
+    B2Z_CUDA(cudaMemcpyAsync(h_out, da.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+}  // extern "C"

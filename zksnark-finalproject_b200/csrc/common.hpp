@@ -1,0 +1,114 @@
+// Library-internal declarations shared by the translation units of libb200zk.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+#include "mont.cuh"
+
+namespace b2z {
+
+struct StatusError {
+  b2z_status code;
+  std::string msg;
+};
+
+#define B2Z_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      throw ::b2z::StatusError{e__ == cudaErrorMemoryAllocation ? B2Z_ENOMEM : B2Z_ECUDA,  \
+                               std::string(#expr) + ": " + cudaGetErrorString(e__)};       \
+  } while (0)
+
+#define B2Z_REQUIRE(cond, code, text)                                  \
+  do {                                                                 \
+    if (!(cond)) throw ::b2z::StatusError{code, std::string(text)};    \
+  } while (0)
+
+// RAII device buffer.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  explicit DevBuf(size_t count) { alloc(count); }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) B2Z_CUDA(cudaMalloc(&p, count * sizeof(T)));
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// ---------------------------------------------------------------------------
+// NTT (ntt.cu)
+// ---------------------------------------------------------------------------
+enum TwKind { TW_FWD = 0, TW_INV = 1, TW_COSET_FWD = 2, TW_COSET_INV = 3, TW_KINDS = 4 };
+
+// Per-domain-size twiddle tables, level-major: level L (butterfly half-size 2^L)
+// occupies entries [2^L - 1, 2^(L+1) - 1); n - 1 entries per kind.
+struct NttDomain {
+  uint32_t log_n = 0;
+  DevBuf<FrEl> tw[TW_KINDS];
+  FrEl n_inv;            // n^-1                     (Montgomery)
+  FrEl wm_k1, wm_k2;     // n^-3 Z^-1, n^-2 Z^-1     (witness-map pointwise constants)
+};
+
+struct Ctx;
+const NttDomain& ntt_domain(Ctx* ctx, uint32_t log_n);
+const FrEl* ntt_twiddles(Ctx* ctx, uint32_t log_n, TwKind kind, cudaStream_t st);
+
+// natural -> bit-reversed
+void ntt_dif(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
+// bit-reversed -> natural
+void ntt_dit(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
+// DIF with tw_a then DIT with tw_b (natural -> natural), low stages fused in one kernel
+void ntt_dif_dit(const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st);
+// in-place bit-reversal permutation; if scale != nullptr every element is also
+// multiplied by *scale (host value); if pw_lo/pw_hi != nullptr additionally by
+// pw_lo[i & 1023] * pw_hi[i >> 10] with i the NATURAL (destination) index.
+void ntt_bitrev(FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
+// data[i] *= pw_lo[i & 1023] * pw_hi[i >> 10]
+void ntt_scale_powers(FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
+// out[j] = base^j, j < count
+void fr_pow_table(FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st);
+// a <- a*b*k1 - c*k2   (witness-map pointwise step, constants folded)
+void wm_pointwise(FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2, cudaStream_t st);
+// canonicalise (lazy -> [0, p)) in place
+void fr_canonicalize(FrEl* data, size_t n, cudaStream_t st);
+
+// Full witness map on device buffers a, b, c (natural order, destroyed); h is
+// left in `a`, in bit-reversed order if !natural_out.
+void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  std::mutex mu;                       // one in-flight call per context (see include/b200zk.h)
+  cudaStream_t stream = nullptr;
+  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::map<uint32_t, NttDomain> domains;
+  void* msm_scratch = nullptr;         // MsmScratch arenas (msm.cu)
+  void* fixed_base = nullptr;          // generator tables (msm.cu)
+  std::string last_error;
+};
+
+}  // namespace b2z

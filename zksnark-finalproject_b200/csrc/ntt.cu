@@ -1,0 +1,440 @@
+// Radix-2 NTT over BLS12-381 Fr for sm_100a -- replaces
+// ark_poly::Radix2EvaluationDomain<Fr>::{fft_in_place, ifft_in_place, get_coset}
+// (ark-poly ^0.4.2, /root/reference/Cargo.toml:43), the seven transforms inside
+// LibsnarkReduction::witness_map_from_matrices.
+//
+// Design (not a translation of ark-poly's serial/rayon butterflies):
+//   * A transform is a decimation-in-frequency (natural -> bit-reversed) or
+//     decimation-in-time (bit-reversed -> natural) network whose log n stages
+//     are grouped into PASSES over HBM.  One pass = one kernel: a CTA stages a
+//     tile of 2^k x C elements in shared memory (k consecutive index bits
+//     [t, t+k), C adjacent columns so that global accesses are contiguous),
+//     runs k stages on it and writes it back.  Inside a pass every thread keeps
+//     8 elements in registers and does 3 stages (12 butterflies) between two
+//     shared-memory exchanges.
+//   * iNTT followed by a coset NTT needs NO bit-reversal and no separate
+//     coset scaling: DIF leaves coefficients bit-reversed, DIT consumes them
+//     that way, the coset powers g^i are folded into the per-level twiddle
+//     tables (level with butterfly size m uses g^(n/m) * w_m^j), and the two
+//     low-bit passes run fused in one kernel on the same tile.
+//   * Twiddles come from per-level tables in HBM/L2 (a 32-byte load is ~100x
+//     cheaper than the 255-bit multiplication that would recompute it).
+//   * n^-1 factors are folded into the witness map's pointwise constants.
+#include "common.hpp"
+
+namespace b2z {
+
+namespace {
+
+constexpr uint32_t kMaxTileLog = 11;   // 2048 elements = 64 KiB of data per CTA
+
+__device__ __forceinline__ uint32_t sm_phys(uint32_t i) { return i + (i >> 3); }
+
+// Shared-memory tile: two planes of 16-byte half-elements, padded 1/8 so that a
+// quarter-warp touching elements at stride 1, 2, 4 or 8 hits 8 distinct 16-byte
+// bank groups.
+struct Tile {
+  uint4* lo;
+  uint4* hi;
+  __device__ __forceinline__ FrEl load(uint32_t i) const {
+    const uint32_t p = sm_phys(i);
+    const uint4 a = lo[p], b = hi[p];
+    FrEl r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ void store(uint32_t i, const FrEl& v) const {
+    const uint32_t p = sm_phys(i);
+    lo[p] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    hi[p] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  }
+};
+
+__device__ __forceinline__ FrEl ldg_fr(const FrEl* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 a = __ldg(q), b = __ldg(q + 1);
+  FrEl r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ FrEl ld_fr(const FrEl* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 a = q[0], b = q[1];
+  FrEl r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void st_fr(FrEl* p, const FrEl& v) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// Geometry of one pass: index bits [t, t+k) are transformed, C = 2^logC adjacent
+// low columns ride along for coalescing (logC <= t).
+struct PassGeom {
+  uint32_t t, k, logC;
+};
+
+// One exchange round: Q stages on local bits [p0, p0+Q) of the tile's k-bit row
+// index.  Each thread owns 8 elements: 8 >> Q groups of 2^Q.
+template <int Q, bool DIT>
+__device__ __forceinline__ void ntt_round(const Tile& tile, const FrEl* __restrict__ tw, PassGeom g, uint32_t p0,
+                                          uint32_t col_base) {
+  constexpr int R = 1 << Q;
+  constexpr int G = 8 >> Q;
+  const uint32_t ngroups = (1u << (g.k + g.logC)) >> Q;
+  const uint32_t cmask = (1u << g.logC) - 1;
+#pragma unroll 1
+  for (int gi = 0; gi < G; gi++) {
+    const uint32_t gid = threadIdx.x + gi * blockDim.x;
+    if (gid < ngroups) {
+      const uint32_t c = gid & cmask;
+      const uint32_t rest = gid >> g.logC;
+      const uint32_t blow = rest & ((1u << p0) - 1);
+      const uint32_t bhigh = rest >> p0;
+      const uint32_t row0 = (bhigh << (p0 + Q)) | blow;
+      FrEl x[R];
+#pragma unroll
+      for (int e = 0; e < R; e++) x[e] = tile.load((((row0 | ((uint32_t)e << p0))) << g.logC) | c);
+#pragma unroll
+      for (int s = 0; s < Q; s++) {
+        const int r = DIT ? s : Q - 1 - s;
+        const uint32_t lvl = g.t + p0 + r;
+        const FrEl* twl = tw + ((1u << lvl) - 1);
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+          if (e & (1 << r)) continue;
+          const uint32_t j = ((blow | ((uint32_t)(e & ((1 << r) - 1)) << p0)) << g.t) | (col_base + c);
+          const FrEl w = ldg_fr(twl + j);
+          FrEl& u = x[e];
+          FrEl& v = x[e | (1 << r)];
+          if (DIT) {
+            const FrEl tv = Fr::mul(w, v);
+            v = Fr::sub(u, tv);
+            u = Fr::add(u, tv);
+          } else {
+            const FrEl d = Fr::sub(u, v);
+            u = Fr::add(u, v);
+            v = Fr::mul(w, d);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < R; e++) tile.store((((row0 | ((uint32_t)e << p0))) << g.logC) | c, x[e]);
+    }
+  }
+  __syncthreads();
+}
+
+template <bool DIT>
+__device__ __forceinline__ void ntt_round_q(int q, const Tile& tile, const FrEl* tw, PassGeom g, uint32_t p0,
+                                            uint32_t col_base) {
+  if (q == 3) ntt_round<3, DIT>(tile, tw, g, p0, col_base);
+  else if (q == 2) ntt_round<2, DIT>(tile, tw, g, p0, col_base);
+  else ntt_round<1, DIT>(tile, tw, g, p0, col_base);
+}
+
+// All k stages of a pass on the tile in shared memory.
+template <bool DIT>
+__device__ __forceinline__ void ntt_tile_stages(const Tile& tile, const FrEl* tw, PassGeom g, uint32_t col_base) {
+  if (DIT) {
+    uint32_t p0 = 0;
+    while (p0 < g.k) {
+      const int q = (g.k - p0 >= 3) ? 3 : (int)(g.k - p0);
+      ntt_round_q<true>(q, tile, tw, g, p0, col_base);
+      p0 += q;
+    }
+  } else {
+    uint32_t top = g.k;
+    while (top > 0) {
+      const int q = top >= 3 ? 3 : (int)top;
+      ntt_round_q<false>(q, tile, tw, g, top - q, col_base);
+      top -= q;
+    }
+  }
+}
+
+enum PassMode { PASS_DIF = 0, PASS_DIT = 1, PASS_DIF_DIT = 2 };
+
+// grid = n / 2^(k+logC) tiles; block = max(32, tile/8) threads;
+// dynamic smem = 2 * (S + S/8) * 16 bytes.
+template <int MODE>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(FrEl* __restrict__ data, const FrEl* __restrict__ tw_a,
+                                                       const FrEl* __restrict__ tw_b, PassGeom g) {
+  extern __shared__ uint4 smem[];
+  const uint32_t S = 1u << (g.k + g.logC);
+  Tile tile{smem, smem + S + (S >> 3)};
+  const uint32_t ltiles_log = g.t - g.logC;
+  const uint32_t tileL = blockIdx.x & ((1u << ltiles_log) - 1);
+  const uint64_t H = blockIdx.x >> ltiles_log;
+  const uint32_t col_base = tileL << g.logC;
+  FrEl* base = data + ((H << (g.t + g.k)) | col_base);
+  const uint32_t cmask = (1u << g.logC) - 1;
+  for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+    const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
+    tile.store(i, ld_fr(base + off));
+  }
+  __syncthreads();
+  if (MODE == PASS_DIF) ntt_tile_stages<false>(tile, tw_a, g, col_base);
+  if (MODE == PASS_DIT) ntt_tile_stages<true>(tile, tw_a, g, col_base);
+  if (MODE == PASS_DIF_DIT) {
+    ntt_tile_stages<false>(tile, tw_a, g, col_base);
+    ntt_tile_stages<true>(tile, tw_b, g, col_base);
+  }
+  for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+    const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
+    st_fr(base + off, tile.load(i));
+  }
+}
+
+template <int MODE>
+void launch_pass(FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint32_t log_n, PassGeom g, cudaStream_t st) {
+  const uint32_t ls = g.k + g.logC;
+  const uint32_t S = 1u << ls;
+  const uint32_t threads = S / 8 < 32 ? 32 : S / 8;
+  const size_t smem = (size_t)2 * (S + (S >> 3)) * sizeof(uint4);
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[MODE]) {
+    B2Z_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  2 * ((1 << kMaxTileLog) + (1 << (kMaxTileLog - 3))) * (int)sizeof(uint4)));
+    attr_set[MODE] = true;
+  }
+  const uint32_t grid = 1u << (log_n - ls);
+  ntt_pass_kernel<MODE><<<grid, threads, smem, st>>>(data, tw_a, tw_b, g);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+// Pass plan: bits [0, k0) are the contiguous low pass; the remaining high bits
+// are split into passes of at most kMaxTileLog bits, each padded with columns up
+// to the tile size.
+struct Plan {
+  int npass = 0;
+  PassGeom pass[4];   // pass[0] = low bits, ascending
+};
+
+Plan make_plan(uint32_t log_n) {
+  Plan p;
+  uint32_t k0 = log_n < kMaxTileLog ? log_n : kMaxTileLog;
+  p.pass[p.npass++] = PassGeom{0, k0, 0};
+  uint32_t t = k0;
+  uint32_t rem = log_n - k0;
+  const uint32_t nhi = (rem + kMaxTileLog - 1) / kMaxTileLog;
+  for (uint32_t i = 0; i < nhi; i++) {
+    const uint32_t k = (rem + (nhi - i) - 1) / (nhi - i);   // balanced split
+    uint32_t logC = kMaxTileLog - k;
+    if (logC > t) logC = t;
+    p.pass[p.npass++] = PassGeom{t, k, logC};
+    t += k;
+    rem -= k;
+  }
+  return p;
+}
+
+__global__ void bitrev_kernel(FrEl* data, uint32_t log_n, FrEl scale, int has_scale, const FrEl* __restrict__ pw_lo,
+                              const FrEl* __restrict__ pw_hi) {
+  const uint64_t n = 1ull << log_n;
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t j = log_n == 0 ? 0 : (__brevll(i) >> (64 - log_n));
+  if (j < i) return;
+  // element stored at i belongs at natural index j and vice versa
+  FrEl vi = ld_fr(data + i);
+  FrEl vj = ld_fr(data + j);
+  if (has_scale) { vi = Fr::mul(scale, vi); vj = Fr::mul(scale, vj); }
+  if (pw_lo != nullptr) {
+    // vi lands at index j, vj at index i
+    FrEl wj = Fr::mul(Fr::reduce(ldg_fr(pw_lo + (j & 1023))), ldg_fr(pw_hi + (j >> 10)));
+    FrEl wi = Fr::mul(Fr::reduce(ldg_fr(pw_lo + (i & 1023))), ldg_fr(pw_hi + (i >> 10)));
+    vi = Fr::mul(Fr::reduce(wj), vi);
+    vj = Fr::mul(Fr::reduce(wi), vj);
+  }
+  vi = Fr::reduce(vi);
+  vj = Fr::reduce(vj);
+  st_fr(data + j, vi);
+  if (i != j) st_fr(data + i, vj);
+}
+
+__global__ void scale_powers_kernel(FrEl* data, uint64_t n, const FrEl* __restrict__ pw_lo,
+                                    const FrEl* __restrict__ pw_hi) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const FrEl w = Fr::mul(Fr::reduce(ldg_fr(pw_lo + (i & 1023))), ldg_fr(pw_hi + (i >> 10)));
+  st_fr(data + i, Fr::mul(Fr::reduce(w), ld_fr(data + i)));
+}
+
+__global__ void pow_table_kernel(FrEl* out, FrEl base, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  st_fr(out + i, Fr::reduce(Fr::pow_u64(base, i)));
+}
+
+// out[j] = shift * root^j for j < 2^lvl, canonical
+__global__ void twiddle_level_kernel(FrEl* out, FrEl root, FrEl shift, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  st_fr(out + i, Fr::reduce(Fr::mul_safe(Fr::pow_u64(root, i), shift)));
+}
+
+__global__ void wm_pointwise_kernel(FrEl* a, const FrEl* __restrict__ b, const FrEl* __restrict__ c, uint64_t n,
+                                    FrEl k1, FrEl k2) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const FrEl ab = Fr::mul(Fr::reduce(ld_fr(a + i)), ld_fr(b + i));
+  const FrEl t1 = Fr::mul(k1, ab);
+  const FrEl t2 = Fr::mul(k2, ld_fr(c + i));
+  st_fr(a + i, Fr::sub(t1, t2));
+}
+
+__global__ void canonicalize_kernel(FrEl* data, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fr(data + i, Fr::reduce(ld_fr(data + i)));
+}
+
+inline uint32_t blocks_for(uint64_t n, uint32_t threads) { return (uint32_t)((n + threads - 1) / threads); }
+
+FrEl fr_from_u64_host(uint64_t v) {
+  FrEl x = Fr::zero();
+  x.l[0] = (uint32_t)v;
+  x.l[1] = (uint32_t)(v >> 32);
+  return Fr::reduce(Fr::to_mont(x));
+}
+
+FrEl fr_const(uint32_t (*f)(int)) {
+  FrEl x;
+  for (int i = 0; i < 8; i++) x.l[i] = f(i);
+  return x;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// Host-visible launchers
+// ---------------------------------------------------------------------------
+void ntt_dif(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
+  if (log_n == 0) return;
+  const Plan p = make_plan(log_n);
+  for (int i = p.npass - 1; i >= 0; i--) launch_pass<PASS_DIF>(data, tw, nullptr, log_n, p.pass[i], st);
+}
+
+void ntt_dit(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
+  if (log_n == 0) return;
+  const Plan p = make_plan(log_n);
+  for (int i = 0; i < p.npass; i++) launch_pass<PASS_DIT>(data, tw, nullptr, log_n, p.pass[i], st);
+}
+
+void ntt_dif_dit(const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st) {
+  if (log_n == 0) return;
+  const Plan p = make_plan(log_n);
+  for (int i = p.npass - 1; i >= 1; i--) launch_pass<PASS_DIF>(data, tw_a, nullptr, log_n, p.pass[i], st);
+  launch_pass<PASS_DIF_DIT>(data, tw_a, tw_b, log_n, p.pass[0], st);
+  for (int i = 1; i < p.npass; i++) launch_pass<PASS_DIT>(data, tw_b, nullptr, log_n, p.pass[i], st);
+}
+
+void ntt_bitrev(FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi,
+                cudaStream_t st) {
+  const uint64_t n = 1ull << log_n;
+  FrEl s = scale ? *scale : Fr::one();
+  bitrev_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, log_n, s, scale != nullptr, pw_lo, pw_hi);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+void ntt_scale_powers(FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st) {
+  const uint64_t n = 1ull << log_n;
+  scale_powers_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, n, pw_lo, pw_hi);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+void fr_pow_table(FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st) {
+  pow_table_kernel<<<blocks_for(count, 128), 128, 0, st>>>(out, base, count);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+void wm_pointwise(FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2,
+                  cudaStream_t st) {
+  const uint64_t n = 1ull << log_n;
+  wm_pointwise_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, b, c, n, k1, k2);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+void fr_canonicalize(FrEl* data, size_t n, cudaStream_t st) {
+  if (n == 0) return;
+  canonicalize_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, n);
+  B2Z_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// Domains and twiddle tables
+// ---------------------------------------------------------------------------
+const NttDomain& ntt_domain(Ctx* ctx, uint32_t log_n) {
+  auto it = ctx->domains.find(log_n);
+  if (it != ctx->domains.end()) return it->second;
+  NttDomain& d = ctx->domains[log_n];
+  d.log_n = log_n;
+  const FrEl n_mont = fr_from_u64_host(1ull << log_n);
+  d.n_inv = Fr::reduce(Fr::inv(n_mont));
+  // Z_H(g) = g^n - 1 on the coset g = 7  (evaluate_vanishing_polynomial, A.2)
+  const FrEl g = fr_const(FrParams::generator);
+  FrEl gn = g;
+  for (uint32_t i = 0; i < log_n; i++) gn = Fr::sqr(gn);
+  const FrEl z = Fr::reduce(Fr::sub(gn, Fr::one()));
+  const FrEl zinv = Fr::reduce(Fr::inv(z));
+  const FrEl n2 = Fr::reduce(Fr::sqr(d.n_inv));
+  d.wm_k2 = Fr::reduce(Fr::mul(n2, zinv));
+  d.wm_k1 = Fr::reduce(Fr::mul(d.n_inv, d.wm_k2));
+  return d;
+}
+
+const FrEl* ntt_twiddles(Ctx* ctx, uint32_t log_n, TwKind kind, cudaStream_t st) {
+  NttDomain& d = const_cast<NttDomain&>(ntt_domain(ctx, log_n));
+  if (d.tw[kind].p != nullptr || log_n == 0) return d.tw[kind].p;
+  const uint64_t n = 1ull << log_n;
+  d.tw[kind].alloc(n);   // n - 1 used
+  const bool inverse = (kind == TW_INV || kind == TW_COSET_INV);
+  const bool coset = (kind == TW_COSET_FWD || kind == TW_COSET_INV);
+  const FrEl root32 = fr_const(FrParams::root_of_unity);
+  FrEl g = fr_const(FrParams::generator);
+  if (inverse) g = Fr::reduce(Fr::inv(g));
+  for (uint32_t lvl = 0; lvl < log_n; lvl++) {
+    // butterfly size m = 2^(lvl+1): root = w_m^(+-1), shift = g^(+-n/m)
+    FrEl root = root32;
+    for (uint32_t i = 0; i < 32 - (lvl + 1); i++) root = Fr::sqr(root);
+    root = Fr::reduce(root);
+    if (inverse) root = Fr::reduce(Fr::inv(root));
+    FrEl shift = Fr::one();
+    if (coset) {
+      shift = g;
+      for (uint32_t i = 0; i < log_n - (lvl + 1); i++) shift = Fr::sqr(shift);
+    }
+    shift = Fr::reduce(shift);
+    const uint32_t count = 1u << lvl;
+    twiddle_level_kernel<<<blocks_for(count, 128), 128, 0, st>>>(d.tw[kind].p + (count - 1), root, shift, count);
+    B2Z_CUDA(cudaGetLastError());
+  }
+  return d.tw[kind].p;
+}
+
+// ---------------------------------------------------------------------------
+// Witness map (A.3): h = iNTT_coset( (NTT_coset(iNTT a) * NTT_coset(iNTT b)
+//                                     - NTT_coset(iNTT c)) / Z_H(g) )
+// All n^-1 factors and Z^-1 are folded into wm_k1, wm_k2.
+// ---------------------------------------------------------------------------
+void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st) {
+  const NttDomain& d = ntt_domain(ctx, log_n);
+  const FrEl* tw_inv = ntt_twiddles(ctx, log_n, TW_INV, st);
+  const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
+  const FrEl* tw_ci = ntt_twiddles(ctx, log_n, TW_COSET_INV, st);
+  ntt_dif_dit(tw_inv, tw_cf, a, log_n, st);
+  ntt_dif_dit(tw_inv, tw_cf, b, log_n, st);
+  ntt_dif_dit(tw_inv, tw_cf, c, log_n, st);
+  wm_pointwise(a, b, c, log_n, d.wm_k1, d.wm_k2, st);
+  ntt_dif(tw_ci, a, log_n, st);
+  if (natural_out) ntt_bitrev(a, log_n, nullptr, nullptr, nullptr, st);
+  else fr_canonicalize(a, (size_t)1 << log_n, st);
+}
+
+}  // namespace b2z

@@ -1,0 +1,318 @@
+"""Host-side mirror of the arkworks surface the reference's prove routes call,
+implemented over the C ABI of libb200zk (include/b200zk.h).
+
+The reference is Rust; this container has no Rust toolchain, so the host side
+above the C ABI is written in Python with the same names, argument meaning and
+error behaviour as the arkworks items it stands in for, and the Rust binding a
+maintainer would add is shown in INTEGRATION.md.
+
+  Radix2EvaluationDomain    ark_poly::Radix2EvaluationDomain<Fr>
+  LibsnarkReduction         ark_groth16::r1cs_to_qap::LibsnarkReduction
+  VariableBaseMSM           ark_ec::VariableBaseMSM (msm_bigint for G1 / G2)
+  FixedBase                 ark_ec::scalar_mul::fixed_base::FixedBase
+  ProvingKey / Groth16      ark_groth16::{ProvingKey, Groth16::prove,
+                            create_random_proof_with_reduction,
+                            create_proof_with_reduction}
+  (call sites: src/arkworks/backend/fibbonaci_handler.rs:110,
+   matrix_proof.rs:139-140, prime_snark.rs:119)
+
+Nothing here computes on the CPU: every method forwards to CUDA through the C
+ABI and raises if the library or the GPU is missing.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _ffi, codec
+from .codec import R_MOD
+
+FR_GENERATOR = 7          # ark_bls12_381::Fr::GENERATOR, the coset offset LibsnarkReduction uses
+
+
+class SynthesisError(Exception):
+    """ark_relations::r1cs::SynthesisError (only the variants the path can raise)."""
+
+
+class PolynomialDegreeTooLarge(SynthesisError):
+    pass
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(ctypes.c_void_p) if arr is not None else None
+
+
+def _fr_array(x):
+    a = np.ascontiguousarray(x, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("expected an (n, 4) uint64 array of Fr limbs")
+    return a
+
+
+class Context:
+    """One b2z_ctx: a CUDA device plus its streams, twiddle tables and scratch."""
+
+    def __init__(self, device=0):
+        self._lib = _ffi.lib()
+        h = ctypes.c_void_p()
+        st = self._lib.b2z_ctx_create(int(device), ctypes.byref(h))
+        if st != _ffi.B2Z_OK:
+            raise _ffi.B2zError(st, "b2z_ctx_create(device=%d) failed (no CUDA device? there is no CPU fallback)" % device)
+        self.handle = h
+        self.device = device
+
+    def check(self, st):
+        if st == _ffi.B2Z_OK:
+            return
+        msg = self._lib.b2z_last_error(self.handle).decode(errors="replace")
+        if st == _ffi.B2Z_ESIZE:
+            raise PolynomialDegreeTooLarge(msg)
+        raise _ffi.B2zError(st, msg)
+
+    def close(self):
+        if self.handle:
+            self._lib.b2z_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Radix2EvaluationDomain:
+    """ark_poly::Radix2EvaluationDomain<Fr>: size = next power of two >= num_coeffs."""
+
+    def __init__(self, ctx, num_coeffs, offset=None):
+        size, log = 1, 0
+        while size < num_coeffs:
+            size <<= 1
+            log += 1
+        if log > 32:                       # Fr::TWO_ADICITY
+            raise PolynomialDegreeTooLarge("domain of %d coefficients exceeds 2^32" % num_coeffs)
+        self.ctx, self.size, self.log_size_of_group = ctx, size, log
+        self.offset = offset               # None = base domain, else canonical int
+
+    @classmethod
+    def new(cls, ctx, num_coeffs):
+        return cls(ctx, num_coeffs)
+
+    def get_coset(self, offset):
+        return Radix2EvaluationDomain(self.ctx, self.size, int(offset) % R_MOD)
+
+    def _run(self, evals, inverse):
+        a = _fr_array(evals)
+        if a.shape[0] > self.size:
+            raise ValueError("input longer than the domain")
+        if a.shape[0] < self.size:         # arkworks zero-pads
+            a = np.concatenate([a, np.zeros((self.size - a.shape[0], 4), np.uint64)])
+        a = np.ascontiguousarray(a).copy()
+        g = None
+        if self.offset is not None and self.offset != 1:
+            g = codec.fr_to_mont_limbs([self.offset])
+        self.ctx.check(self.ctx._lib.b2z_ntt_fr(self.ctx.handle, _ptr(a), self.log_size_of_group, int(inverse), _ptr(g)))
+        return a
+
+    def fft(self, coeffs):
+        """coefficients -> evaluations over (offset *) <w>, natural order; returns a new array."""
+        return self._run(coeffs, False)
+
+    def ifft(self, evals):
+        return self._run(evals, True)
+
+
+def evaluate_constraint(terms, assignment):
+    """ark_groth16::r1cs_to_qap::evaluate_constraint (host side, exact integers)."""
+    acc = 0
+    for coeff, index in terms:
+        acc += coeff * assignment[index]
+    return acc % R_MOD
+
+
+class LibsnarkReduction:
+    """ark_groth16::r1cs_to_qap::LibsnarkReduction (the R1CSToQAP the reference uses)."""
+
+    @staticmethod
+    def constraint_evaluations(matrices, num_inputs, num_constraints, full_assignment):
+        """The a, b, c vectors witness_map_from_matrices builds before its FFTs,
+        as Montgomery limb arrays of the domain size."""
+        a_m, b_m, c_m = matrices
+        size = 1
+        while size < num_constraints + num_inputs:
+            size <<= 1
+        a = [0] * size
+        b = [0] * size
+        c = [0] * size
+        for i in range(num_constraints):
+            a[i] = evaluate_constraint(a_m[i], full_assignment)
+            b[i] = evaluate_constraint(b_m[i], full_assignment)
+            c[i] = evaluate_constraint(c_m[i], full_assignment)
+        for j in range(num_inputs):
+            a[num_constraints + j] = full_assignment[j] % R_MOD
+        return codec.fr_to_mont_limbs(a), codec.fr_to_mont_limbs(b), codec.fr_to_mont_limbs(c)
+
+    @staticmethod
+    def witness_map_from_evaluations(ctx, a, b, c):
+        a, b, c = _fr_array(a), _fr_array(b), _fr_array(c)
+        n = a.shape[0]
+        if n & (n - 1) or b.shape[0] != n or c.shape[0] != n:
+            raise ValueError("a, b, c must have the same power-of-two length")
+        h = np.empty_like(a)
+        ctx.check(ctx._lib.b2z_witness_map(ctx.handle, _ptr(a), _ptr(b), _ptr(c), n.bit_length() - 1, _ptr(h)))
+        return h
+
+    @staticmethod
+    def witness_map_from_matrices(ctx, matrices, num_inputs, num_constraints, full_assignment):
+        """h coefficients (Montgomery limbs, length = domain size)."""
+        if (num_constraints + num_inputs - 1).bit_length() > 32:
+            raise PolynomialDegreeTooLarge("domain exceeds 2^32")
+        a, b, c = LibsnarkReduction.constraint_evaluations(matrices, num_inputs, num_constraints, full_assignment)
+        return LibsnarkReduction.witness_map_from_evaluations(ctx, a, b, c)
+
+
+class VariableBaseMSM:
+    """ark_ec::VariableBaseMSM for G1Projective / G2Projective."""
+
+    @staticmethod
+    def _run(ctx, fn, bases, inf, scalars, width):
+        bases = np.ascontiguousarray(bases, dtype=np.uint64)
+        scalars = _fr_array(scalars)
+        n = min(bases.shape[0], scalars.shape[0])          # msm_bigint truncates to the shorter
+        out = np.zeros(3 * width, dtype=np.uint64)
+        infp = np.ascontiguousarray(inf, dtype=np.uint8) if inf is not None else None
+        ctx.check(fn(ctx.handle, _ptr(bases), _ptr(infp), _ptr(scalars), n, _ptr(out)))
+        return out
+
+    @staticmethod
+    def msm_bigint_g1(ctx, bases, scalars, inf=None):
+        """bases (n, 12) Montgomery limbs, scalars (n, 4) canonical limbs -> 18 limbs (X, Y, Z)."""
+        return VariableBaseMSM._run(ctx, ctx._lib.b2z_msm_g1, bases, inf, scalars, 6)
+
+    @staticmethod
+    def msm_bigint_g2(ctx, bases, scalars, inf=None):
+        return VariableBaseMSM._run(ctx, ctx._lib.b2z_msm_g2, bases, inf, scalars, 12)
+
+    @staticmethod
+    def msm_g1(ctx, bases, scalars, inf=None):
+        """`msm`: unlike msm_bigint, a length mismatch is an error (Err(min_len) in arkworks)."""
+        if len(bases) != len(scalars):
+            raise ValueError("length mismatch: %d" % min(len(bases), len(scalars)))
+        return VariableBaseMSM.msm_bigint_g1(ctx, bases, scalars, inf)
+
+
+class FixedBase:
+    """ark_ec::scalar_mul::fixed_base::FixedBase::msm on the standard generators."""
+
+    @staticmethod
+    def msm_g1(ctx, scalars):
+        s = _fr_array(scalars)
+        n = s.shape[0]
+        out = np.zeros((n, 12), dtype=np.uint64)
+        inf = np.zeros((n + 7) // 8, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_fixed_base_mul_g1(ctx.handle, _ptr(s), n, _ptr(out), _ptr(inf)))
+        return out, inf
+
+    @staticmethod
+    def msm_g2(ctx, scalars):
+        s = _fr_array(scalars)
+        n = s.shape[0]
+        out = np.zeros((n, 24), dtype=np.uint64)
+        inf = np.zeros((n + 7) // 8, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_fixed_base_mul_g2(ctx.handle, _ptr(s), n, _ptr(out), _ptr(inf)))
+        return out, inf
+
+
+class ProvingKey:
+    """ark_groth16::ProvingKey<Bls12_381> as packed limb arrays, plus its device copy."""
+
+    FIELDS = ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query")
+
+    def __init__(self, num_variables, num_instance, domain_size, a_query, b_g1_query, b_g2_query, h_query, l_query,
+                 alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2):
+        """Each query is (limbs ndarray, identity bitmap | None); the five single
+        points are limb arrays of 12 (G1) / 24 (G2) uint64."""
+        self.num_variables, self.num_instance, self.domain_size = num_variables, num_instance, domain_size
+        self.a_query, self.b_g1_query, self.b_g2_query = a_query, b_g1_query, b_g2_query
+        self.h_query, self.l_query = h_query, l_query
+        self.alpha_g1, self.beta_g1, self.delta_g1 = alpha_g1, beta_g1, delta_g1
+        self.beta_g2, self.delta_g2 = beta_g2, delta_g2
+        self._ctx = None
+        self._handle = None
+
+    def upload(self, ctx):
+        """b2z_pk_upload: copies the key to the device (once per circuit)."""
+        if self._handle is not None:
+            return self
+        keep = []
+
+        def q(pair):
+            arr = np.ascontiguousarray(pair[0], dtype=np.uint64)
+            inf = np.ascontiguousarray(pair[1], dtype=np.uint8) if pair[1] is not None else None
+            keep.extend([arr, inf])
+            return _ptr(arr) if arr.size else None, _ptr(inf) if inf is not None and inf.size else None
+
+        def p(arr):
+            arr = np.ascontiguousarray(arr, dtype=np.uint64)
+            keep.append(arr)
+            return _ptr(arr)
+
+        d = _ffi.PkDesc()
+        d.num_variables, d.num_instance = self.num_variables, self.num_instance
+        d.log_domain = self.domain_size.bit_length() - 1
+        d.a_query, d.a_inf = q(self.a_query)
+        d.b_g1_query, d.b_g1_inf = q(self.b_g1_query)
+        d.b_g2_query, d.b_g2_inf = q(self.b_g2_query)
+        d.h_query, d.h_inf = q(self.h_query)
+        d.l_query, d.l_inf = q(self.l_query)
+        d.alpha_g1, d.beta_g1, d.delta_g1 = p(self.alpha_g1), p(self.beta_g1), p(self.delta_g1)
+        d.beta_g2, d.delta_g2 = p(self.beta_g2), p(self.delta_g2)
+        h = ctypes.c_void_p()
+        ctx.check(ctx._lib.b2z_pk_upload(ctx.handle, ctypes.byref(d), ctypes.byref(h)))
+        self._ctx, self._handle = ctx, h
+        return self
+
+    def free(self):
+        if self._handle is not None and self._ctx is not None and self._ctx.handle:
+            self._ctx._lib.b2z_pk_free(self._ctx.handle, self._handle)
+        self._handle = None
+
+
+class Groth16:
+    """ark_groth16::Groth16::<Bls12_381> -- the proving half."""
+
+    @staticmethod
+    def create_proof_with_reduction(ctx, pk, a, b, c, full_assignment, r, s):
+        """create_proof_with_reduction after synthesis: a/b/c evaluation vectors and the
+        full assignment as Montgomery limb arrays; r, s canonical ints (the two draws
+        `create_random_proof_with_reduction` makes).  Returns the 192 bytes of
+        Proof::serialize_compressed."""
+        pk.upload(ctx)
+        a, b, c, z = _fr_array(a), _fr_array(b), _fr_array(c), _fr_array(full_assignment)
+        if a.shape[0] != pk.domain_size or b.shape[0] != pk.domain_size or c.shape[0] != pk.domain_size:
+            raise ValueError("evaluation vectors must have the key's domain size")
+        if z.shape[0] != pk.num_variables:
+            raise ValueError("assignment length != number of variables")
+        rs = codec.fr_to_mont_limbs([r, s])
+        out = np.zeros(192, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_groth16_prove(ctx.handle, pk._handle, _ptr(a), _ptr(b), _ptr(c), _ptr(z),
+                                             _ptr(rs[0:1]), _ptr(rs[1:2]), _ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
+    def create_random_proof_with_reduction(ctx, pk, matrices, num_constraints, full_assignment_ints, rng):
+        """Draws r then s from `rng` (a callable returning canonical Fr ints, in the
+        order ark-groth16 draws them), evaluates the constraint rows on the host and proves."""
+        r = rng()
+        s = rng()
+        a, b, c = LibsnarkReduction.constraint_evaluations(matrices, pk.num_instance, num_constraints,
+                                                           full_assignment_ints)
+        z = codec.fr_to_mont_limbs(full_assignment_ints)
+        return Groth16.create_proof_with_reduction(ctx, pk, a, b, c, z, r, s)
+
+    prove = create_random_proof_with_reduction
