@@ -138,6 +138,22 @@ B2Z_API b2z_status b2z_fixed_base_mul_g1(b2z_ctx* ctx, const uint64_t* scalars, 
 B2Z_API b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t n,
                                          uint64_t* out_points, uint8_t* out_inf);
 
+/* ---- measurement hooks ----------------------------------------------------------------
+ * Phase timers use CUDA events recorded on the stream each kernel is launched on.
+ * Phases (index into the arrays of b2z_profile_read, length B2Z_PHASE_COUNT):
+ *   0 NTT pass kernels (units: field elements)   1 witness-map pointwise (elements)
+ *   2 MSM digits + counting sort (scalars)       3 MSM bucket accumulation G1 (mixed adds)
+ *   4 MSM bucket accumulation G2 (mixed adds)    5 MSM partial lists / bucket reduction / combine
+ *   6 proof finalisation (scalar muls, affine, serialization)                            */
+#define B2Z_PHASE_COUNT 8
+B2Z_API b2z_status b2z_profile_enable(b2z_ctx* ctx, int on);
+B2Z_API b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset);
+/* kernels launched through this context since its creation */
+B2Z_API uint64_t b2z_kernel_launches(const b2z_ctx* ctx);
+/* measured 32-bit multiply-add issue rates of the device (ops/s): plain IMAD and the
+ * carry-chained 32x32+64 wide form the field arithmetic is built from               */
+B2Z_API b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
+
 /* ---- host-side self checks (no GPU needed) -------------------------------------------
  * The limb algorithms of the device code are written against a carry-flag
  * abstraction that also runs on the host; these entry points let the CPU-only test

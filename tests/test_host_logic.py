@@ -1,0 +1,160 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and
+exports what include/b200zk.h declares, fails loudly without a GPU, and the
+limb algorithms of the device code (run through the host carry-flag emulation)
+agree with the oracle."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import bls12_381 as O
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_header_symbols_are_exported(b2z):
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    declared = set(re.findall(r"B2Z_API\s+[\w\s\*]+?\b(b2z_\w+)\s*\(", hdr))
+    assert len(declared) >= 17
+    L = ctypes.CDLL(b2z._ffi.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), "header declares %s but the library does not export it" % name
+    assert declared == set(b2z._ffi.SIGNATURES), "ctypes table out of sync with the header"
+
+
+def test_no_cpu_fallback_without_gpu(b2z):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present")
+    with pytest.raises(b2z._ffi.B2zError) as e:
+        b2z.Context(0)
+    assert e.value.status == b2z._ffi.B2Z_ECUDA
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "zksnark-finalproject_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".inc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "ark_cpu" not in txt, f
+
+
+def _arr32(x, n):
+    return np.array([(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)], dtype=np.uint32)
+
+
+def _val(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+@pytest.mark.parametrize("field,p,n", [(0, O.R_MOD, 8), (1, O.Q_MOD, 12)])
+def test_device_field_arithmetic_on_host(b2z, field, p, n):
+    L = b2z._ffi.lib()
+    R = 1 << (32 * n)
+    rnd = random.Random(field)
+    edge = [0, 1, p - 1, p, p + 1, 2 * p - 1]
+    for it in range(3000):
+        a = rnd.choice(edge) if rnd.random() < 0.15 else rnd.randrange(2 * p)
+        b = rnd.choice(edge) if rnd.random() < 0.15 else rnd.randrange(2 * p)
+        A, B = _arr32(a, n), _arr32(b, n)
+        out = np.zeros(n, dtype=np.uint32)
+        for op, want in ((0, a * b * pow(R, -1, p)), (1, a + b), (2, a - b)):
+            assert L.b2z_host_field_op(field, op, A.ctypes.data, B.ctypes.data, out.ctypes.data) == 0
+            r = _val(out)
+            assert r < 2 * p and (r - want) % p == 0, (field, op, hex(a), hex(b))
+        L.b2z_host_field_op(field, 3, A.ctypes.data, None, out.ctypes.data)
+        assert _val(out) == a % p
+        # raw product with the operand precondition of mont.cuh (Fr: first operand canonical)
+        a1 = a % p if field == 0 else a
+        L.b2z_host_field_op(field, 5, _arr32(a1, n).ctypes.data, B.ctypes.data, out.ctypes.data)
+        r = _val(out)
+        assert r < 2 * p and (r * R - a1 * b) % p == 0
+    a = rnd.randrange(1, p)
+    out = np.zeros(n, dtype=np.uint32)
+    L.b2z_host_field_op(field, 4, _arr32(a * R % p, n).ctypes.data, None, out.ctypes.data)
+    assert _val(out) == pow(a, -1, p) * R % p
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_device_point_arithmetic_on_host(b2z, group):
+    L = b2z._ffi.lib()
+    codec = b2z.codec
+    curve = O.G1 if group == 1 else O.G2
+    rnd = random.Random(group)
+    pts = [curve.mul(curve.gen, rnd.randrange(1, 1 << 20)) for _ in range(10)]
+    pts += [pts[0], pts[0], curve.neg(pts[1]), pts[1], pts[4]]          # doubling, cancellation, repeats
+    neg = [rnd.randrange(2) for _ in pts]
+    limbs = (codec.g1_to_limbs if group == 1 else codec.g2_to_limbs)(pts)[0]
+    out = np.zeros(12 * group, dtype=np.uint64)
+    negs = np.array(neg, dtype=np.uint8)
+    rc = L.b2z_host_point_sum(group, limbs.ctypes.data, negs.ctypes.data, len(pts), out.ctypes.data)
+    want = None
+    for p, ng in zip(pts, neg):
+        want = curve.add(want, curve.neg(p) if ng else p)
+    assert rc == 0
+    got = (codec.g1_from_limbs if group == 1 else codec.g2_from_limbs)(out.reshape(1, -1))[0]
+    assert got == want
+    two = (codec.g1_to_limbs if group == 1 else codec.g2_to_limbs)([pts[3], pts[3]])[0]
+    rc = L.b2z_host_point_sum(group, two.ctypes.data, np.array([0, 1], dtype=np.uint8).ctypes.data, 2, out.ctypes.data)
+    assert rc == 1                                                          # P + (-P) is the identity
+
+
+@pytest.mark.parametrize("c", [4, 5, 8, 11, 13, 15, 16, 17, 20])
+def test_msm_digit_recoding(b2z, c):
+    L = b2z._ffi.lib()
+    rnd = random.Random(c)
+    cases = [0, 1, O.R_MOD - 1, (1 << 254), (1 << 254) + (1 << 253)] + [rnd.randrange(O.R_MOD) for _ in range(300)]
+    cases += [rnd.randrange(1 << 16) for _ in range(50)]
+    for k in cases:
+        d = np.zeros(64, dtype=np.int32)
+        w = L.b2z_host_msm_digits(_arr32(k % O.R_MOD, 8).ctypes.data, c, d.ctypes.data)
+        assert sum(int(d[i]) << (c * i) for i in range(w)) == k % O.R_MOD
+        assert all(-(1 << (c - 1)) < int(d[i]) <= (1 << (c - 1)) for i in range(w))     # fits 2^(c-1) buckets
+        assert int(d[w - 1]) >= 0
+
+
+def test_codec_roundtrip(b2z):
+    codec = b2z.codec
+    rnd = random.Random(1)
+    v = [0, 1, O.R_MOD - 1] + [rnd.randrange(O.R_MOD) for _ in range(20)]
+    assert codec.fr_from_mont_limbs(codec.fr_to_mont_limbs(v)) == v
+    assert codec.fr_from_bigint_limbs(codec.fr_to_bigint_limbs(v)) == v
+    # Montgomery one = R mod r
+    assert codec.fr_to_mont_limbs([1])[0].tolist() == [0x00000001FFFFFFFE, 0x5884B7FA00034802, 0x998C4FEFECBC4FF5,
+                                                        0x1824B159ACC5056F]
+    pts = [O.G1_GEN, None, O.G1.mul(O.G1_GEN, 77)]
+    L, inf = codec.g1_to_limbs(pts)
+    assert codec.g1_from_limbs(L, inf) == pts and L.shape == (3, 12)
+    pts2 = [O.G2_GEN, None]
+    L2, inf2 = codec.g2_to_limbs(pts2)
+    assert codec.g2_from_limbs(L2, inf2) == pts2 and L2.shape == (2, 24)
+
+
+def test_circuit_shapes(circuits):
+    fib = circuits.fibonacci_circuit(0, 1, 1000)                # BASELINE config 1
+    assert (fib.num_constraints, fib.num_instance, fib.num_witness, fib.domain_size) == (1001, 4, 1, 1024)
+    assert fib.is_satisfied() and fib.a[0] == [] and fib.b[0] == [(1, 0)]
+    for n in (2, 3, 4):
+        m = circuits.matrix_circuit([[i * n + j for j in range(n)] for i in range(n)], [[1] * n for _ in range(n)])
+        assert m.num_constraints == circuits.matrix_constraint_count(n) and m.num_instance == 4
+        assert m.is_satisfied()
+    assert circuits.matrix_constraint_count(16) == 109955 and circuits.matrix_constraint_count(64) == 2152451
+    p = circuits.prime_circuit(5, num_bits=8, sha_blocks=1)
+    assert p.is_satisfied() and p.num_instance == 4
+    bools = sum(1 for v in p.z if v in (0, 1))
+    assert bools > 0.6 * len(p.z)
+
+
+def test_domain_too_large_maps_to_polynomial_degree_too_large(b2z):
+    with pytest.raises(b2z.PolynomialDegreeTooLarge):
+        b2z.Radix2EvaluationDomain(None, (1 << 32) + 1)
+    assert issubclass(b2z.PolynomialDegreeTooLarge, b2z.SynthesisError)

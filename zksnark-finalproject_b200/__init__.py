@@ -4,4 +4,4 @@ the reference's prove routes use.  Import never touches the GPU; the first
 Context() does, and raises if the library or a device is missing."""
 from . import _ffi, codec                                   # noqa: F401
 from .groth16 import (Context, FixedBase, Groth16, LibsnarkReduction, PolynomialDegreeTooLarge,  # noqa: F401
-                      ProvingKey, Radix2EvaluationDomain, SynthesisError, VariableBaseMSM)
+                      ProvingKey, Radix2EvaluationDomain, SynthesisError, VariableBaseMSM, VerifyingKey)

@@ -42,6 +42,43 @@ void b2z_ctx_destroy(b2z_ctx* ctx) {
   delete ctx;
 }
 
+b2z_status b2z_profile_enable(b2z_ctx* ctx, int on) {
+  return guarded(ctx, [&](Ctx& c) { c.profile = on != 0; });
+}
+
+b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(ms && launches && units, B2Z_EINVAL, "b2z_profile_read: NULL argument");
+    B2Z_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < PH_COUNT; i++) { ms[i] = 0; launches[i] = 0; units[i] = 0; }
+    std::lock_guard<std::mutex> lock(c.span_mu);
+    for (auto& sp : c.spans) {
+      float t = 0;
+      B2Z_CUDA(cudaEventElapsedTime(&t, sp.start, sp.stop));
+      ms[sp.phase] += t;
+      launches[sp.phase] += 1;
+      units[sp.phase] += sp.units_pinned ? *sp.units_pinned : sp.units;
+    }
+    if (reset) {
+      for (auto& sp : c.spans) {
+        cudaEventDestroy(sp.start);
+        cudaEventDestroy(sp.stop);
+        if (sp.units_pinned) cudaFreeHost(sp.units_pinned);
+      }
+      c.spans.clear();
+    }
+  });
+}
+
+uint64_t b2z_kernel_launches(const b2z_ctx* ctx) { return ctx ? ctx->impl.launches : 0; }
+
+b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double* imad_wide_per_s) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(imad_per_s && imad_wide_per_s, B2Z_EINVAL, "b2z_measure_int_peak: NULL argument");
+    measure_int_peak(&c, imad_per_s, imad_wide_per_s);
+  });
+}
+
 const char* b2z_last_error(const b2z_ctx* ctx) { return ctx ? ctx->impl.last_error.c_str() : "null context"; }
 
 b2z_status b2z_ntt_fr(b2z_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse, const uint64_t coset_gen[4]) {
@@ -67,17 +104,17 @@ b2z_status b2z_ntt_fr(b2z_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse,
       const uint32_t nhi = (uint32_t)((n + 1023) >> 10);
       pw_lo.alloc(1024);
       pw_hi.alloc(nhi);
-      fr_pow_table(pw_lo.p, g, 1024, st);
-      fr_pow_table(pw_hi.p, g1024, nhi, st);
+      fr_pow_table(&c, pw_lo.p, g, 1024, st);
+      fr_pow_table(&c, pw_hi.p, g1024, nhi, st);
     }
     if (!inverse) {
-      if (coset) ntt_scale_powers(d.p, log_n, pw_lo.p, pw_hi.p, st);
-      ntt_dif(ntt_twiddles(&c, log_n, TW_FWD, st), d.p, log_n, st);
-      ntt_bitrev(d.p, log_n, nullptr, nullptr, nullptr, st);
+      if (coset) ntt_scale_powers(&c, d.p, log_n, pw_lo.p, pw_hi.p, st);
+      ntt_dif(&c, ntt_twiddles(&c, log_n, TW_FWD, st), d.p, log_n, st);
+      ntt_bitrev(&c, d.p, log_n, nullptr, nullptr, nullptr, st);
     } else {
-      ntt_dif(ntt_twiddles(&c, log_n, TW_INV, st), d.p, log_n, st);
+      ntt_dif(&c, ntt_twiddles(&c, log_n, TW_INV, st), d.p, log_n, st);
       const NttDomain& dom = ntt_domain(&c, log_n);
-      ntt_bitrev(d.p, log_n, &dom.n_inv, coset ? pw_lo.p : nullptr, coset ? pw_hi.p : nullptr, st);
+      ntt_bitrev(&c, d.p, log_n, &dom.n_inv, coset ? pw_lo.p : nullptr, coset ? pw_hi.p : nullptr, st);
     }
     B2Z_CUDA(cudaMemcpyAsync(data, d.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
     B2Z_CUDA(cudaStreamSynchronize(st));

@@ -27,6 +27,13 @@ struct StatusError {
                                std::string(#expr) + ": " + cudaGetErrorString(e__)};       \
   } while (0)
 
+// after every kernel launch: count it and surface launch errors
+#define B2Z_LAUNCHED(ctx_ptr)              \
+  do {                                     \
+    (ctx_ptr)->launches++;                 \
+    B2Z_CUDA(cudaGetLastError());          \
+  } while (0)
+
 #define B2Z_REQUIRE(cond, code, text)                                  \
   do {                                                                 \
     if (!(cond)) throw ::b2z::StatusError{code, std::string(text)};    \
@@ -70,28 +77,60 @@ struct NttDomain {
   FrEl wm_k1, wm_k2;     // n^-3 Z^-1, n^-2 Z^-1     (witness-map pointwise constants)
 };
 
+// ---------------------------------------------------------------------------
+// Profiling spans (CUDA events on the launching stream) and launch counting
+// ---------------------------------------------------------------------------
+enum Phase {
+  PH_NTT_PASS = 0,      // every NTT pass kernel            units: field elements
+  PH_WM_POINTWISE = 1,  // witness-map pointwise kernel     units: field elements
+  PH_MSM_SORT = 2,      // digits + counting sort           units: scalars
+  PH_MSM_ACCUM_G1 = 3,  // bucket accumulation kernel, G1   units: mixed additions
+  PH_MSM_ACCUM_G2 = 4,  // bucket accumulation kernel, G2   units: mixed additions
+  PH_MSM_REDUCE = 5,    // partial lists, bucket reduction, window combine
+  PH_FINALIZE = 6,      // scalar muls, final sums, affine + serialization
+  PH_COUNT = 8
+};
+
+struct ProfileSpan {
+  int phase;
+  cudaEvent_t start, stop;
+  uint64_t units;
+  uint32_t* units_pinned;   // optional: filled by an async D2H copy (actual entry count)
+};
+
 struct Ctx;
+struct ProfileScope {
+  Ctx* ctx;
+  cudaStream_t st;
+  int idx = -1;
+  ProfileScope(Ctx* c, int phase, cudaStream_t s, uint64_t units, const uint32_t* d_units = nullptr);
+  ~ProfileScope();
+};
+
 const NttDomain& ntt_domain(Ctx* ctx, uint32_t log_n);
 const FrEl* ntt_twiddles(Ctx* ctx, uint32_t log_n, TwKind kind, cudaStream_t st);
 
 // natural -> bit-reversed
-void ntt_dif(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
+void ntt_dif(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
 // bit-reversed -> natural
-void ntt_dit(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
+void ntt_dit(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st);
 // DIF with tw_a then DIT with tw_b (natural -> natural), low stages fused in one kernel
-void ntt_dif_dit(const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st);
+void ntt_dif_dit(Ctx* ctx, const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st);
 // in-place bit-reversal permutation; if scale != nullptr every element is also
 // multiplied by *scale (host value); if pw_lo/pw_hi != nullptr additionally by
 // pw_lo[i & 1023] * pw_hi[i >> 10] with i the NATURAL (destination) index.
-void ntt_bitrev(FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
+void ntt_bitrev(Ctx* ctx, FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
 // data[i] *= pw_lo[i & 1023] * pw_hi[i >> 10]
-void ntt_scale_powers(FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
+void ntt_scale_powers(Ctx* ctx, FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st);
 // out[j] = base^j, j < count
-void fr_pow_table(FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st);
+void fr_pow_table(Ctx* ctx, FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st);
 // a <- a*b*k1 - c*k2   (witness-map pointwise step, constants folded)
-void wm_pointwise(FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2, cudaStream_t st);
+void wm_pointwise(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2, cudaStream_t st);
 // canonicalise (lazy -> [0, p)) in place
-void fr_canonicalize(FrEl* data, size_t n, cudaStream_t st);
+void fr_canonicalize(Ctx* ctx, FrEl* data, size_t n, cudaStream_t st);
+
+// 32-bit multiply-add issue rates (ops/s): plain IMAD and the carry-chained wide form
+void measure_int_peak(Ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
 
 // Full witness map on device buffers a, b, c (natural order, destroyed); h is
 // left in `a`, in bit-reversed order if !natural_out.
@@ -106,6 +145,10 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<uint32_t, NttDomain> domains;
+  bool profile = false;
+  std::vector<ProfileSpan> spans;
+  std::mutex span_mu;                  // spans are appended from the single calling thread; guards reads
+  uint64_t launches = 0;               // kernels launched through this context
   void* msm_scratch = nullptr;         // MsmScratch arenas (msm.cu)
   void* fixed_base = nullptr;          // generator tables (msm.cu)
   std::string last_error;

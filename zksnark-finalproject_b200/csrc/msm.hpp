@@ -104,11 +104,11 @@ void msm_release_scratch(Ctx* ctx);
 
 // r (device XYZZ[count]) -> affine limbs + infinity flags on the host side layout
 template <class C>
-void xyzz_to_affine_device(const typename C::Xyzz* d_in, typename C::Affine* d_out, uint32_t* d_inf, uint32_t count,
+void xyzz_to_affine_device(Ctx* ctx, const typename C::Xyzz* d_in, typename C::Affine* d_out, uint32_t* d_inf, uint32_t count,
                            cudaStream_t st);
 
 // Fr Montgomery -> canonical integers (scalars for the MSM), out-of-place.
-void fr_from_mont_device(const FrEl* in, FrEl* out, size_t n, cudaStream_t st);
+void fr_from_mont_device(Ctx* ctx, const FrEl* in, FrEl* out, size_t n, cudaStream_t st);
 
 // out[i] = scalars[i] * G (standard generator), affine; scalars canonical.
 void g1_fixed_base_mul_device(Ctx* ctx, const FrEl* d_scalars, G1::Affine* d_out, uint32_t* d_inf_words, uint32_t n,

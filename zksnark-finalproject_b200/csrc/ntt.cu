@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) ntt_pass_kernel(FrEl* __restrict__ data, 
 }
 
 template <int MODE>
-void launch_pass(FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint32_t log_n, PassGeom g, cudaStream_t st) {
+void launch_pass(Ctx* ctx, FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint32_t log_n, PassGeom g, cudaStream_t st) {
   const uint32_t ls = g.k + g.logC;
   const uint32_t S = 1u << ls;
   const uint32_t threads = S / 8 < 32 ? 32 : S / 8;
@@ -204,8 +204,9 @@ void launch_pass(FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint32_t log_n,
     attr_set[MODE] = true;
   }
   const uint32_t grid = 1u << (log_n - ls);
+  ProfileScope ps(ctx, PH_NTT_PASS, st, (uint64_t)1 << log_n);
   ntt_pass_kernel<MODE><<<grid, threads, smem, st>>>(data, tw_a, tw_b, g);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
 // Pass plan: bits [0, k0) are the contiguous low pass; the remaining high bits
@@ -315,56 +316,57 @@ FrEl fr_const(uint32_t (*f)(int)) {
 // ---------------------------------------------------------------------------
 // Host-visible launchers
 // ---------------------------------------------------------------------------
-void ntt_dif(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
+void ntt_dif(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
   if (log_n == 0) return;
   const Plan p = make_plan(log_n);
-  for (int i = p.npass - 1; i >= 0; i--) launch_pass<PASS_DIF>(data, tw, nullptr, log_n, p.pass[i], st);
+  for (int i = p.npass - 1; i >= 0; i--) launch_pass<PASS_DIF>(ctx, data, tw, nullptr, log_n, p.pass[i], st);
 }
 
-void ntt_dit(const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
+void ntt_dit(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
   if (log_n == 0) return;
   const Plan p = make_plan(log_n);
-  for (int i = 0; i < p.npass; i++) launch_pass<PASS_DIT>(data, tw, nullptr, log_n, p.pass[i], st);
+  for (int i = 0; i < p.npass; i++) launch_pass<PASS_DIT>(ctx, data, tw, nullptr, log_n, p.pass[i], st);
 }
 
-void ntt_dif_dit(const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st) {
+void ntt_dif_dit(Ctx* ctx, const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st) {
   if (log_n == 0) return;
   const Plan p = make_plan(log_n);
-  for (int i = p.npass - 1; i >= 1; i--) launch_pass<PASS_DIF>(data, tw_a, nullptr, log_n, p.pass[i], st);
-  launch_pass<PASS_DIF_DIT>(data, tw_a, tw_b, log_n, p.pass[0], st);
-  for (int i = 1; i < p.npass; i++) launch_pass<PASS_DIT>(data, tw_b, nullptr, log_n, p.pass[i], st);
+  for (int i = p.npass - 1; i >= 1; i--) launch_pass<PASS_DIF>(ctx, data, tw_a, nullptr, log_n, p.pass[i], st);
+  launch_pass<PASS_DIF_DIT>(ctx, data, tw_a, tw_b, log_n, p.pass[0], st);
+  for (int i = 1; i < p.npass; i++) launch_pass<PASS_DIT>(ctx, data, tw_b, nullptr, log_n, p.pass[i], st);
 }
 
-void ntt_bitrev(FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi,
+void ntt_bitrev(Ctx* ctx, FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi,
                 cudaStream_t st) {
   const uint64_t n = 1ull << log_n;
   FrEl s = scale ? *scale : Fr::one();
   bitrev_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, log_n, s, scale != nullptr, pw_lo, pw_hi);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
-void ntt_scale_powers(FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st) {
+void ntt_scale_powers(Ctx* ctx, FrEl* data, uint32_t log_n, const FrEl* pw_lo, const FrEl* pw_hi, cudaStream_t st) {
   const uint64_t n = 1ull << log_n;
   scale_powers_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, n, pw_lo, pw_hi);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
-void fr_pow_table(FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st) {
+void fr_pow_table(Ctx* ctx, FrEl* out, const FrEl& base, uint32_t count, cudaStream_t st) {
   pow_table_kernel<<<blocks_for(count, 128), 128, 0, st>>>(out, base, count);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
-void wm_pointwise(FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2,
+void wm_pointwise(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, const FrEl& k1, const FrEl& k2,
                   cudaStream_t st) {
   const uint64_t n = 1ull << log_n;
+  ProfileScope ps(ctx, PH_WM_POINTWISE, st, n);
   wm_pointwise_kernel<<<blocks_for(n, 256), 256, 0, st>>>(a, b, c, n, k1, k2);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
-void fr_canonicalize(FrEl* data, size_t n, cudaStream_t st) {
+void fr_canonicalize(Ctx* ctx, FrEl* data, size_t n, cudaStream_t st) {
   if (n == 0) return;
   canonicalize_kernel<<<blocks_for(n, 256), 256, 0, st>>>(data, n);
-  B2Z_CUDA(cudaGetLastError());
+  B2Z_LAUNCHED(ctx);
 }
 
 // ---------------------------------------------------------------------------
@@ -413,7 +415,7 @@ const FrEl* ntt_twiddles(Ctx* ctx, uint32_t log_n, TwKind kind, cudaStream_t st)
     shift = Fr::reduce(shift);
     const uint32_t count = 1u << lvl;
     twiddle_level_kernel<<<blocks_for(count, 128), 128, 0, st>>>(d.tw[kind].p + (count - 1), root, shift, count);
-    B2Z_CUDA(cudaGetLastError());
+    B2Z_LAUNCHED(ctx);
   }
   return d.tw[kind].p;
 }
@@ -428,13 +430,114 @@ void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, boo
   const FrEl* tw_inv = ntt_twiddles(ctx, log_n, TW_INV, st);
   const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
   const FrEl* tw_ci = ntt_twiddles(ctx, log_n, TW_COSET_INV, st);
-  ntt_dif_dit(tw_inv, tw_cf, a, log_n, st);
-  ntt_dif_dit(tw_inv, tw_cf, b, log_n, st);
-  ntt_dif_dit(tw_inv, tw_cf, c, log_n, st);
-  wm_pointwise(a, b, c, log_n, d.wm_k1, d.wm_k2, st);
-  ntt_dif(tw_ci, a, log_n, st);
-  if (natural_out) ntt_bitrev(a, log_n, nullptr, nullptr, nullptr, st);
-  else fr_canonicalize(a, (size_t)1 << log_n, st);
+  ntt_dif_dit(ctx, tw_inv, tw_cf, a, log_n, st);
+  ntt_dif_dit(ctx, tw_inv, tw_cf, b, log_n, st);
+  ntt_dif_dit(ctx, tw_inv, tw_cf, c, log_n, st);
+  wm_pointwise(ctx, a, b, c, log_n, d.wm_k1, d.wm_k2, st);
+  ntt_dif(ctx, tw_ci, a, log_n, st);
+  if (natural_out) ntt_bitrev(ctx, a, log_n, nullptr, nullptr, nullptr, st);
+  else fr_canonicalize(ctx, a, (size_t)1 << log_n, st);
+}
+
+// ---------------------------------------------------------------------------
+// Profiling spans
+// ---------------------------------------------------------------------------
+ProfileScope::ProfileScope(Ctx* c, int phase, cudaStream_t s, uint64_t units, const uint32_t* d_units)
+    : ctx(c), st(s) {
+  if (!c->profile) return;
+  ProfileSpan sp;
+  sp.phase = phase;
+  sp.units = units;
+  sp.units_pinned = nullptr;
+  B2Z_CUDA(cudaEventCreate(&sp.start));
+  B2Z_CUDA(cudaEventCreate(&sp.stop));
+  if (d_units != nullptr) {
+    B2Z_CUDA(cudaMallocHost(&sp.units_pinned, sizeof(uint32_t)));
+    *sp.units_pinned = 0;
+    // the count is produced by an earlier kernel on the same stream
+    B2Z_CUDA(cudaMemcpyAsync(sp.units_pinned, d_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  }
+  B2Z_CUDA(cudaEventRecord(sp.start, s));
+  std::lock_guard<std::mutex> lock(c->span_mu);
+  c->spans.push_back(sp);
+  idx = (int)c->spans.size() - 1;
+}
+
+ProfileScope::~ProfileScope() {
+  if (idx < 0) return;
+  cudaEventRecord(ctx->spans[idx].stop, st);
+}
+
+// ---------------------------------------------------------------------------
+// Integer-pipe peak: register-resident multiply-add chains at full occupancy.
+// Gives the denominators of the MSM / NTT integer rooflines.
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int kPeakIters = 4096, kPeakChains = 8;
+
+__global__ void __launch_bounds__(256) imad_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t x[kPeakChains];
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) x[j] = threadIdx.x + j;
+#pragma unroll 1
+  for (int i = 0; i < kPeakIters; i++) {
+#pragma unroll
+    for (int j = 0; j < kPeakChains; j++) x[j] = x[j] * a + b;     // IMAD
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) s ^= x[j];
+  if (s == 0x12345678u) out[0] = s;
+}
+
+// the instruction the field multiplications are made of: (lo, hi) += a*b with carry in/out
+__global__ void __launch_bounds__(256) imad_wide_peak_kernel(uint32_t* out, uint32_t a, uint32_t b) {
+  uint32_t lo[kPeakChains], hi[kPeakChains];
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) { lo[j] = threadIdx.x + j; hi[j] = j; }
+  ptx::CF cf;
+#pragma unroll 1
+  for (int i = 0; i < kPeakIters; i++) {
+    ptx::mad_wide_cc(cf, lo[0], hi[0], a, b);
+#pragma unroll
+    for (int j = 1; j < kPeakChains; j++) ptx::madc_wide_cc(cf, lo[j], hi[j], a, b);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kPeakChains; j++) s ^= lo[j] ^ hi[j];
+  if (s == 0x12345678u) out[0] = s;
+}
+}  // namespace
+
+void measure_int_peak(Ctx* ctx, double* imad_per_s, double* imad_wide_per_s) {
+  cudaStream_t st = ctx->stream;
+  int sms = 0;
+  B2Z_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+  DevBuf<uint32_t> out(1);
+  const int grid = sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  B2Z_CUDA(cudaEventCreate(&e0));
+  B2Z_CUDA(cudaEventCreate(&e1));
+  double best[2] = {0, 0};
+  for (int which = 0; which < 2; which++) {
+    for (int rep = 0; rep < 5; rep++) {
+      B2Z_CUDA(cudaEventRecord(e0, st));
+      if (which == 0) imad_peak_kernel<<<grid, block, 0, st>>>(out.p, 0x9e3779b1u + rep, 0x7f4a7c15u);
+      else imad_wide_peak_kernel<<<grid, block, 0, st>>>(out.p, 0x9e3779b1u + rep, 0x7f4a7c15u);
+      B2Z_LAUNCHED(ctx);
+      B2Z_CUDA(cudaEventRecord(e1, st));
+      B2Z_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      B2Z_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double ops = (double)grid * block * kPeakIters * kPeakChains;
+      const double rate = ops / (ms * 1e-3);
+      if (rep > 0 && rate > best[which]) best[which] = rate;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *imad_per_s = best[0];
+  *imad_wide_per_s = best[1];
 }
 
 }  // namespace b2z

@@ -266,7 +266,7 @@ void msm_entry(Ctx& c, const uint64_t* bases, const uint8_t* inf_bitmap, const u
   DevBuf<Affine> aff(1);
   DevBuf<uint32_t> flag(1);
   msm_run<C>(&c, 0, B, ds.p, (uint32_t)n, nullptr, res.p, st);
-  xyzz_to_affine_device<C>(res.p, aff.p, flag.p, 1, st);
+  xyzz_to_affine_device<C>(&c, res.p, aff.p, flag.p, 1, st);
   Affine h_aff;
   uint32_t h_flag = 0;
   B2Z_CUDA(cudaMemcpyAsync(&h_aff, aff.p, sizeof(Affine), cudaMemcpyDeviceToHost, st));
@@ -314,27 +314,36 @@ void prove_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrE
   FrEl tail_h[4] = {one_c, r_c, one_c, s_c};   // {1, r} for A ; {1, s} for B1, B2
   B2Z_CUDA(cudaMemcpyAsync(pk.tail.p, tail_h, sizeof(tail_h), cudaMemcpyHostToDevice, c.aux[0]));
   // z -> canonical
-  fr_from_mont_device(d_z, pk.zc.p, m, c.aux[0]);
+  fr_from_mont_device(&c, d_z, pk.zc.p, m, c.aux[0]);
   B2Z_CUDA(cudaEventRecord(pk.ev_z, c.aux[0]));
   G1::Xyzz* g1o = pk.g1_out.p;
   // A (aux0), B1 (aux1), B2 (aux2), L (aux3)
   msm_run<G1>(&c, 1, pk.a, pk.zc.p, (uint32_t)m, pk.tail.p, g1o + 0, c.aux[0]);
-  scalar_mul_kernel<G1><<<1, 32, 0, c.aux[0]>>>(g1o + 0, s_c, g1o + 4);
+  {
+    ProfileScope ps(&c, PH_FINALIZE, c.aux[0], 1);
+    scalar_mul_kernel<G1><<<1, 32, 0, c.aux[0]>>>(g1o + 0, s_c, g1o + 4);
+    B2Z_LAUNCHED(&c);
+  }
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], c.aux[0]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], pk.ev_z, 0));
   msm_run<G1>(&c, 2, pk.b1, pk.zc.p, (uint32_t)m, pk.tail.p + 2, g1o + 1, c.aux[1]);
-  scalar_mul_kernel<G1><<<1, 32, 0, c.aux[1]>>>(g1o + 1, r_c, g1o + 5);
+  {
+    ProfileScope ps(&c, PH_FINALIZE, c.aux[1], 1);
+    scalar_mul_kernel<G1><<<1, 32, 0, c.aux[1]>>>(g1o + 1, r_c, g1o + 5);
+    B2Z_LAUNCHED(&c);
+  }
   B2Z_CUDA(cudaEventRecord(pk.ev_done[1], c.aux[1]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[2], pk.ev_z, 0));
   msm_run<G2>(&c, 3, pk.b2, pk.zc.p, (uint32_t)m, pk.tail.p + 2, pk.g2_out.p, c.aux[2]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], c.aux[2]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[3], pk.ev_z, 0));
   scalar_mul_kernel<G1><<<1, 32, 0, c.aux[3]>>>(g1o + 7, rs_c, g1o + 6);
+  B2Z_LAUNCHED(&c);
   msm_run<G1>(&c, 4, pk.lq, pk.zc.p + l, (uint32_t)(m - l), nullptr, g1o + 2, c.aux[3]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], c.aux[3]));
   // witness map + H on the main stream
   witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);
-  fr_from_mont_device(d_a, pk.hc.p, (size_t)1 << pk.log_n, st);
+  fr_from_mont_device(&c, d_a, pk.hc.p, (size_t)1 << pk.log_n, st);
   msm_run<G1>(&c, 0, pk.h, pk.hc.p, 1u << pk.log_n, nullptr, g1o + 3, st);
   for (auto& e : pk.ev_done) B2Z_CUDA(cudaStreamWaitEvent(st, e, 0));
   FinalizeArgs fa;
@@ -342,8 +351,11 @@ void prove_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrE
   fa.rsD = g1o + 6;
   fa.B2 = pk.g2_out.p;
   fa.out = pk.proof.p;
-  groth16_finalize_kernel<<<1, 32, 0, st>>>(fa);
-  B2Z_CUDA(cudaGetLastError());
+  {
+    ProfileScope ps(&c, PH_FINALIZE, st, 1);
+    groth16_finalize_kernel<<<1, 32, 0, st>>>(fa);
+    B2Z_LAUNCHED(&c);
+  }
   B2Z_CUDA(cudaMemcpyAsync(pk.h_proof, pk.proof.p, 192, cudaMemcpyDeviceToHost, st));
   B2Z_CUDA(cudaStreamSynchronize(st));
   std::memcpy(proof_out, pk.h_proof, 192);
@@ -414,6 +426,7 @@ b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
       permute_bitrev_g1_kernel<<<nblk(n, 256), 256, 0, st>>>(src.p, src_inf.p, (uint32_t)(n - 1), P.log_n, dst.p,
                                                              flags.p);
       pack_flags_kernel2<<<nblk((n + 31) / 32, 128), 128, 0, st>>>(flags.p, (uint32_t)n, words.p);
+      c.launches += 2;
       B2Z_CUDA(cudaGetLastError());
       msm_bases_build<G1>(&c, P.h, dst.p, words.p, (uint32_t)n, pre, 0, st);
       B2Z_CUDA(cudaStreamSynchronize(st));

@@ -283,8 +283,92 @@ class ProvingKey:
         self._handle = None
 
 
+class VerifyingKey:
+    """ark_groth16::VerifyingKey<Bls12_381> (limb arrays; only what verification needs)."""
+
+    def __init__(self, alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1):
+        self.alpha_g1, self.beta_g2, self.gamma_g2, self.delta_g2 = alpha_g1, beta_g2, gamma_g2, delta_g2
+        self.gamma_abc_g1 = gamma_abc_g1          # (limbs (l, 12), identity bitmap)
+
+
+def _batch_inverse(values):
+    """Montgomery's trick over Fr (host integers)."""
+    pref, acc = [], 1
+    for v in values:
+        pref.append(acc)
+        acc = acc * v % R_MOD
+    inv = pow(acc, -1, R_MOD)
+    out = [0] * len(values)
+    for i in range(len(values) - 1, -1, -1):
+        out[i] = inv * pref[i] % R_MOD
+        inv = inv * values[i] % R_MOD
+    return out
+
+
+FR_TWO_ADIC_ROOT = pow(FR_GENERATOR, (R_MOD - 1) >> 32, R_MOD)
+
+
 class Groth16:
-    """ark_groth16::Groth16::<Bls12_381> -- the proving half."""
+    """ark_groth16::Groth16::<Bls12_381> -- key generation and the proving half."""
+
+    @staticmethod
+    def generate_parameters_with_qap(ctx, matrices, num_constraints, num_instance, num_variables,
+                                     alpha, beta, gamma, delta, tau):
+        """ark_groth16 generator.rs `generate_parameters_with_qap` with the STANDARD
+        generators and caller-supplied toxic waste (Groth16::setup draws these and random
+        generators from its rng; reference call sites fibbonaci_handler.rs:107,
+        matrix_proof.rs:129).  The QAP evaluation at tau (LibsnarkReduction::
+        instance_map_with_evaluation) is exact integer host work; every group element is
+        produced on the GPU by b2z_fixed_base_mul_g1/g2.  Returns (ProvingKey, VerifyingKey)."""
+        a_m, b_m, c_m = matrices
+        l, m = num_instance, num_variables
+        n, log_n = 1, 0
+        while n < num_constraints + l:
+            n <<= 1
+            log_n += 1
+        if log_n > 32:
+            raise PolynomialDegreeTooLarge("domain exceeds 2^32")
+        w = pow(FR_TWO_ADIC_ROOT, 1 << (32 - log_n), R_MOD)
+        zt = (pow(tau, n, R_MOD) - 1) % R_MOD
+        if zt == 0:
+            raise ValueError("tau lies in the evaluation domain")
+        # Lagrange coefficients L_i(tau) = Z(tau)/n * w^i / (tau - w^i)
+        ws, cur = [], 1
+        for _ in range(n):
+            ws.append(cur)
+            cur = cur * w % R_MOD
+        dinv = _batch_inverse([(tau - x) % R_MOD for x in ws])
+        zn = zt * pow(n, -1, R_MOD) % R_MOD
+        lag = [zn * x % R_MOD * d % R_MOD for x, d in zip(ws, dinv)]
+        at, bt, ct = [0] * m, [0] * m, [0] * m
+        for j in range(l):
+            at[j] = lag[num_constraints + j]
+        for i in range(num_constraints):
+            u = lag[i]
+            for coeff, col in a_m[i]:
+                at[col] += u * coeff
+            for coeff, col in b_m[i]:
+                bt[col] += u * coeff
+            for coeff, col in c_m[i]:
+                ct[col] += u * coeff
+        at = [x % R_MOD for x in at]
+        bt = [x % R_MOD for x in bt]
+        ct = [x % R_MOD for x in ct]
+        ginv, dinv_ = pow(gamma, -1, R_MOD), pow(delta, -1, R_MOD)
+        abc = [(beta * x + alpha * y + z) % R_MOD for x, y, z in zip(at, bt, ct)]
+        hs, t = [], zt * dinv_ % R_MOD
+        for _ in range(n - 1):
+            hs.append(t)
+            t = t * tau % R_MOD
+        big = codec.fr_to_bigint_limbs
+        g1 = lambda xs: FixedBase.msm_g1(ctx, big(xs)) if xs else (np.zeros((0, 12), np.uint64), None)
+        g2 = lambda xs: FixedBase.msm_g2(ctx, big(xs)) if xs else (np.zeros((0, 24), np.uint64), None)
+        singles1, _ = g1([alpha, beta, delta])
+        singles2, _ = g2([beta, gamma, delta])
+        pk = ProvingKey(m, l, n, g1(at), g1(bt), g2(bt), g1(hs), g1([x * dinv_ % R_MOD for x in abc[l:]]),
+                        singles1[0], singles1[1], singles1[2], singles2[0], singles2[2])
+        vk = VerifyingKey(singles1[0], singles2[0], singles2[1], singles2[2], g1([x * ginv % R_MOD for x in abc[:l]]))
+        return pk, vk
 
     @staticmethod
     def create_proof_with_reduction(ctx, pk, a, b, c, full_assignment, r, s):
