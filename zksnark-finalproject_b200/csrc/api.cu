@@ -20,8 +20,12 @@ b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
   ctx->impl.device = device_id;
   try {
     B2Z_CUDA(cudaSetDevice(device_id));
-    B2Z_CUDA(cudaStreamCreateWithFlags(&ctx->impl.stream, cudaStreamNonBlocking));
-    for (auto& s : ctx->impl.aux) B2Z_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    // the main stream carries the witness map and the MSM that depends on it (the critical
+    // path of a proof): its blocks are scheduled ahead of the z-only MSMs on the aux streams
+    int prio_lo = 0, prio_hi = 0;
+    B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_hi));
+    for (auto& s : ctx->impl.aux) B2Z_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_lo));
   } catch (const StatusError& e) {
     delete ctx;
     return e.code;

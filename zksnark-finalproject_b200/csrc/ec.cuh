@@ -60,6 +60,7 @@ struct XyzzPoint {
 
 template <class F>
 struct Curve {
+  using Fld = F;
   using El = typename F::El;
   using Affine = AffinePoint<F>;
   using Xyzz = XyzzPoint<F>;

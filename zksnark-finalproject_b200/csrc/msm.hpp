@@ -62,8 +62,8 @@ B2Z_HD void for_each_digit(const FrEl& k, const DigitCfg& cfg, Emit&& emit) {
 // Scratch arenas: one per concurrently running MSM (indexed by `slot`).
 struct MsmArena {
   DevBuf<uint32_t> hist, offsets, cursor, tile_sums, sorted;
-  DevBuf<uint32_t> keys[2];
-  DevBuf<uint8_t> buckets, parts[2], chunks[2];
+  DevBuf<uint32_t> keys[2], state;
+  DevBuf<uint8_t> buckets, parts[2], chunks[3], wsums;
 };
 struct MsmScratch {
   MsmArena slot[8];

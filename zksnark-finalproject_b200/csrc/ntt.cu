@@ -219,14 +219,19 @@ struct Plan {
 
 Plan make_plan(uint32_t log_n) {
   Plan p;
-  uint32_t k0 = log_n < kMaxTileLog ? log_n : kMaxTileLog;
+  // tile = 2^ls elements per CTA: full tiles for big transforms, smaller ones for small
+  // transforms so that a 2^16..2^18 NTT still spreads over >= 256 CTAs (148 SMs)
+  uint32_t ls = log_n > 8 ? log_n - 8 : 0;
+  if (ls < 8) ls = 8;
+  if (ls > kMaxTileLog) ls = kMaxTileLog;
+  uint32_t k0 = log_n < ls ? log_n : ls;
   p.pass[p.npass++] = PassGeom{0, k0, 0};
   uint32_t t = k0;
   uint32_t rem = log_n - k0;
-  const uint32_t nhi = (rem + kMaxTileLog - 1) / kMaxTileLog;
+  const uint32_t nhi = (rem + ls - 1) / ls;
   for (uint32_t i = 0; i < nhi; i++) {
     const uint32_t k = (rem + (nhi - i) - 1) / (nhi - i);   // balanced split
-    uint32_t logC = kMaxTileLog - k;
+    uint32_t logC = ls - k;
     if (logC > t) logC = t;
     p.pass[p.npass++] = PassGeom{t, k, logC};
     t += k;
