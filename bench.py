@@ -264,6 +264,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     launches0 = L.b2z_kernel_launches(ctx.handle)
+    print("[bench] library kernels launched before the timed region: %d" % launches0, file=sys.stderr, flush=True)
     L.b2z_profile_enable(ctx.handle, 1)
     clocks = ClockSampler(local_rank)
     clocks.start()

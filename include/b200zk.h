@@ -120,6 +120,23 @@ B2Z_API b2z_status b2z_groth16_prove(b2z_ctx* ctx, const b2z_pk* pk, const uint6
                              const uint64_t* z, const uint64_t r[4], const uint64_t s[4],
                              uint8_t proof_out[192]);
 
+/* ---- point-sharded proving across the GPUs of one box ------------------------------------
+ * An MSM is a sum over independent (scalar, point) pairs, so a proof shards by points
+ * (SURVEY.md 8(e)): rank k of `world` keeps variables [m k/world, m (k+1)/world) of the
+ * a / b_g1 / b_g2 / l queries and the same fraction of the (bit-reversed) h bases; rank 0 also
+ * keeps the alpha/beta/delta terms.  Every rank passes the SAME full desc and the same full
+ * a/b/c/z/r/s; the witness map runs on every rank.  Each rank gets B2Z_PARTIAL_BYTES of partial
+ * sums (XYZZ limbs: A | C_z | C_h in G1, B in G2); gather them over any transport (NCCL
+ * all_gather of 960 bytes per rank) and finish on the host with b2z_groth16_combine.          */
+#define B2Z_PARTIAL_BYTES 960
+B2Z_API b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* desc, uint32_t rank, uint32_t world,
+                                       b2z_pk** out);
+B2Z_API b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk, const uint64_t* a_evals,
+                                             const uint64_t* b_evals, const uint64_t* c_evals, const uint64_t* z,
+                                             const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);
+/* host only (no GPU, no ctx): partials = world x B2Z_PARTIAL_BYTES in rank order */
+B2Z_API b2z_status b2z_groth16_combine(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]);
+
 /* Same computation on inputs already resident in device memory (device pointers
  * on ctx's device; a/b/c are clobbered).  Used to separate kernel time from
  * PCIe time in benchmarks; the proof bytes still land in host memory.            */
@@ -148,6 +165,8 @@ B2Z_API b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, 
 #define B2Z_PHASE_COUNT 8
 B2Z_API b2z_status b2z_profile_enable(b2z_ctx* ctx, int on);
 B2Z_API b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset);
+/* timeline of the recorded spans relative to the first one (development aid); returns the count */
+B2Z_API int b2z_profile_spans(b2z_ctx* ctx, int max_spans, int* phase, double* start_ms, double* stop_ms);
 /* kernels launched through this context since its creation */
 B2Z_API uint64_t b2z_kernel_launches(const b2z_ctx* ctx);
 /* measured 32-bit multiply-add issue rates of the device (ops/s): plain IMAD and the

@@ -339,6 +339,29 @@ def test_prove_matrix_16x16_full_size(b2z, ctx, codec, cpu_oracle, circuits):
     _setup_prove_verify(b2z, ctx, codec, cpu_oracle, inst, 4)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_prove_point_sharded_equals_whole_key(b2z, ctx, codec, circuits, world):
+    """the shards of one key (here all on one GPU, one after the other) produce
+    partial sums whose host combination is byte-identical to the single-GPU proof."""
+    inst = circuits.matrix_circuit([[1, 2, 3], [4, 5, 6], [7, 8, 9]], [[2, 0, 1], [1, 1, 1], [3, 2, 1]])
+    rnd = random.Random(world)
+    toxic = [rnd.randrange(1, R) for _ in range(5)]
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+                                                      inst.num_variables, *toxic)
+    r, s = rnd.randrange(R), rnd.randrange(R)
+    want, (a, b, c) = _prove_gpu(b2z, ctx, codec, pk, inst, r, s)
+    z = codec.fr_to_mont_limbs(inst.z)
+    parts = []
+    for k in range(world):
+        shard = b2z.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                               pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                               pk.beta_g2, pk.delta_g2).upload(ctx, rank=k, world=world)
+        parts.append(b2z.Groth16.create_proof_partial(ctx, shard, a, b, c, z, r, s))
+        shard.free()
+    assert b2z.Groth16.combine(parts) == want
+    pk.free()
+
+
 # ------------------------------------------------------------------------------- error behaviour
 def test_error_codes(b2z, ctx):
     import ctypes

@@ -1,0 +1,35 @@
+#!/bin/bash
+# Profiling evidence for one bench configuration (run under gpurun on ONE GPU).
+#   1. plain run (must exit 0)   2. per-launch durations of one timed step   3. --set full on the top kernels
+set -u
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 3 --cpu-steps 0"
+$CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain.err; exit 1; }
+SKIP=$(grep -o 'before the timed region: [0-9]*' gpurun_out/ncu_plain.err | grep -o '[0-9]*$')
+echo "library kernels before the timed region: $SKIP"
+KREGEX='regex:msm_|ntt_|wm_|scalar_prep|fr_from_mont|canonicalize|scan_|bitrev|pack_flags|fb_|batch_norm|twiddle|pow_table'
+# the timed region of this command is 2 steps of ~83 launches; list one of them (+ a few)
+ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s $SKIP -c 100 --csv \
+    --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?"
+# accumulation launches per proof: A (G1), B (G2), C_z (G1), C_h (G1)  ->  index 14 = C_z, 13 = B
+ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 14 -c 1 \
+    -o gpurun_out/prof_accum_g1 $CMD > gpurun_out/ncu_full_accum_g1.log 2>&1
+echo "full accum g1 exit $?"
+ncu --set full --clock-control none -k regex:msm_accum_kernel -s 13 -c 1 \
+    -o gpurun_out/prof_accum_g2 $CMD > gpurun_out/ncu_full_accum_g2.log 2>&1
+echo "full accum g2 exit $?"
+ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 45 -c 2 \
+    -o gpurun_out/prof_ntt $CMD > gpurun_out/ncu_full_ntt.log 2>&1
+echo "full ntt exit $?"
+for f in prof_accum_g1 prof_accum_g2 prof_ntt; do
+  ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
+  ncu -i gpurun_out/$f.ncu-rep --page details > gpurun_out/$f.details.txt 2>/dev/null
+done
+ncu -i gpurun_out/prof_accum_g1.ncu-rep --page source --csv > gpurun_out/prof_accum_g1.source.csv 2>/dev/null
+ls -la gpurun_out/
+# keep the transfer under the 64 MiB cap
+for f in gpurun_out/*.ncu-rep; do
+  sz=$(stat -c %s "$f"); if [ "$sz" -gt 20000000 ]; then echo "dropping $f ($sz bytes; CSV pages kept)"; rm -f "$f"; fi
+done
+du -sh gpurun_out

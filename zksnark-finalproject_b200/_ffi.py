@@ -6,6 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200zk.so")
 
+PARTIAL_BYTES = 960
 B2Z_OK, B2Z_EINVAL, B2Z_ESIZE, B2Z_ECUDA, B2Z_ENOMEM = 0, 1, 2, 3, 4
 STATUS_NAMES = {0: "B2Z_OK", 1: "B2Z_EINVAL", 2: "B2Z_ESIZE", 3: "B2Z_ECUDA", 4: "B2Z_ENOMEM"}
 
@@ -38,11 +39,16 @@ SIGNATURES = {
     "b2z_pk_upload": (ctypes.c_int32, [vp, ctypes.POINTER(PkDesc), ctypes.POINTER(vp)]),
     "b2z_pk_free": (None, [vp, vp]),
     "b2z_groth16_prove": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2z_pk_upload_shard": (ctypes.c_int32, [vp, ctypes.POINTER(PkDesc), ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.POINTER(vp)]),
+    "b2z_groth16_prove_partial": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2z_groth16_combine": (ctypes.c_int32, [vp, ctypes.c_uint32, vp]),
     "b2z_groth16_prove_device": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2z_fixed_base_mul_g1": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, vp, vp]),
     "b2z_fixed_base_mul_g2": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, vp, vp]),
     "b2z_profile_enable": (ctypes.c_int32, [vp, ctypes.c_int]),
     "b2z_profile_read": (ctypes.c_int32, [vp, vp, vp, vp, ctypes.c_int]),
+    "b2z_profile_spans": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp]),
     "b2z_kernel_launches": (ctypes.c_uint64, [vp]),
     "b2z_measure_int_peak": (ctypes.c_int32, [vp, vp, vp]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),

@@ -25,7 +25,10 @@ b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_hi));
-    for (auto& s : ctx->impl.aux) B2Z_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_lo));
+    // aux[1] carries the G2 MSM, whose tail is the longest: let it finish its accumulation early
+    // so that its bucket reduction overlaps the G1 accumulations instead of trailing them
+    for (int i = 0; i < 4; i++)
+      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
   } catch (const StatusError& e) {
     delete ctx;
     return e.code;
@@ -72,6 +75,26 @@ b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64
       c.spans.clear();
     }
   });
+}
+
+int b2z_profile_spans(b2z_ctx* ctx, int max_spans, int* phase, double* start_ms, double* stop_ms) {
+  int n = 0;
+  guarded(ctx, [&](Ctx& c) {
+    B2Z_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(c.span_mu);
+    if (c.spans.empty()) return;
+    for (auto& sp : c.spans) {
+      if (n >= max_spans) break;
+      float t0 = 0, t1 = 0;
+      B2Z_CUDA(cudaEventElapsedTime(&t0, c.spans[0].start, sp.start));
+      B2Z_CUDA(cudaEventElapsedTime(&t1, c.spans[0].start, sp.stop));
+      phase[n] = sp.phase;
+      start_ms[n] = t0;
+      stop_ms[n] = t1;
+      n++;
+    }
+  });
+  return n;
 }
 
 uint64_t b2z_kernel_launches(const b2z_ctx* ctx) { return ctx ? ctx->impl.launches : 0; }

@@ -198,6 +198,40 @@ inline G1Xyzz g1_add(const G1Xyzz& a, const G1Xyzz& b) {
   return o;
 }
 
+inline Fq2 fq2_add(const Fq2& a, const Fq2& b) { return Fq2{fq_add(a.c0, b.c0), fq_add(a.c1, b.c1)}; }
+inline Fq2 fq2_sub(const Fq2& a, const Fq2& b) { return Fq2{fq_sub(a.c0, b.c0), fq_sub(a.c1, b.c1)}; }
+inline Fq2 fq2_dbl(const Fq2& a) { return fq2_add(a, a); }
+inline G2Xyzz g2_dbl(const G2Xyzz& p) {
+  if (fq2_is_zero(p.zz)) return p;
+  const Fq2 u = fq2_dbl(p.y), v = fq2_sqr(u), w = fq2_mul(u, v), s = fq2_mul(p.x, v), xx = fq2_sqr(p.x);
+  const Fq2 m = fq2_add(fq2_dbl(xx), xx);
+  G2Xyzz r;
+  r.x = fq2_sub(fq2_sqr(m), fq2_dbl(s));
+  r.y = fq2_sub(fq2_mul(m, fq2_sub(s, r.x)), fq2_mul(w, p.y));
+  r.zz = fq2_mul(v, p.zz);
+  r.zzz = fq2_mul(w, p.zzz);
+  return r;
+}
+inline G2Xyzz g2_add(const G2Xyzz& a, const G2Xyzz& b) {
+  if (fq2_is_zero(a.zz)) return b;
+  if (fq2_is_zero(b.zz)) return a;
+  const Fq2 u1 = fq2_mul(a.x, b.zz), u2 = fq2_mul(b.x, a.zz), s1 = fq2_mul(a.y, b.zzz), s2 = fq2_mul(b.y, a.zzz);
+  const Fq2 p = fq2_sub(u2, u1), r = fq2_sub(s2, s1);
+  if (fq2_is_zero(p)) {
+    if (fq2_is_zero(r)) return g2_dbl(a);
+    G2Xyzz id;
+    std::memset(&id, 0, sizeof(id));
+    return id;
+  }
+  const Fq2 pp = fq2_sqr(p), ppp = fq2_mul(p, pp), q = fq2_mul(u1, pp);
+  G2Xyzz o;
+  o.x = fq2_sub(fq2_sub(fq2_sqr(r), ppp), fq2_dbl(q));
+  o.y = fq2_sub(fq2_mul(r, fq2_sub(q, o.x)), fq2_mul(s1, ppp));
+  o.zz = fq2_mul(fq2_mul(a.zz, b.zz), pp);
+  o.zzz = fq2_mul(fq2_mul(a.zzz, b.zzz), ppp);
+  return o;
+}
+
 // affine normalisation (Montgomery coordinates); returns true for the identity
 inline bool g1_to_affine(const G1Xyzz& p, Fq* x, Fq* y) {
   if (fq_is_zero(p.zz)) { *x = fq_zero(); *y = fq_zero(); return true; }

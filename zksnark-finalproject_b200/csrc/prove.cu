@@ -65,31 +65,34 @@ __global__ void pack_flags_kernel2(const uint32_t* flags, uint32_t n, uint32_t* 
 }
 
 struct ScalarPrep {
-  const FrEl* z;     // m Montgomery elements
+  const FrEl* z;     // full assignment, m Montgomery elements
   FrEl* out_a;       // n1 canonical scalars for A
   FrEl* out_c;       // n1 canonical scalars for C_z
-  uint32_t m, l;
+  uint32_t lo, ma;   // this key covers variables [lo, lo + ma) of a_query / b_g1_query
+  uint32_t l_lo, ml; // ... and variables [l_lo, l_lo + ml) of the witness part (l_query)
+  uint32_t with_vk;  // alpha, beta, delta terms live on shard 0 only
   FrEl r, s, rs;     // canonical integers (NOT Montgomery): mont_mul(k, z*R) = k*z
 };
 
-// index space: [0,m) a-part, [m,2m) b1-part, [2m, 3m-l) l-part, then alpha, beta, delta
+// index space: [0,ma) a-part, [ma,2ma) b1-part, [2ma, 2ma+ml) l-part, then (alpha, beta, delta)
 __global__ void scalar_prep_kernel(ScalarPrep a) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t n1 = 3 * a.m - a.l + 3;
+  const uint32_t body = 2 * a.ma + a.ml;
+  const uint32_t n1 = body + (a.with_vk ? 3 : 0);
   if (i >= n1) return;
   FrEl one = Fr::zero();
   one.l[0] = 1;
   FrEl sa = Fr::zero(), sc;
-  if (i < a.m) {
-    const FrEl z = a.z[i];
+  if (i < a.ma) {
+    const FrEl z = a.z[a.lo + i];
     sa = Fr::reduce(Fr::mul(one, z));
     sc = Fr::reduce(Fr::mul(a.s, z));
-  } else if (i < 2 * a.m) {
-    sc = Fr::reduce(Fr::mul(a.r, a.z[i - a.m]));
-  } else if (i < 3 * a.m - a.l) {
-    sc = Fr::reduce(Fr::mul(one, a.z[i - 2 * a.m + a.l]));
+  } else if (i < 2 * a.ma) {
+    sc = Fr::reduce(Fr::mul(a.r, a.z[a.lo + i - a.ma]));
+  } else if (i < body) {
+    sc = Fr::reduce(Fr::mul(one, a.z[a.l_lo + i - 2 * a.ma]));
   } else {
-    const uint32_t k = i - (3 * a.m - a.l);
+    const uint32_t k = i - body;
     sa = k == 0 ? one : (k == 2 ? a.r : Fr::zero());
     sc = k == 0 ? a.s : (k == 1 ? a.r : a.rs);
   }
@@ -113,7 +116,10 @@ FrEl fr_load_host(const uint64_t v[4]) {
 struct PkImpl {
   uint32_t log_n = 0;
   uint64_t m = 0, l = 0;
-  uint32_t n1 = 0;             // 3m - l + 3 bases in g1_all
+  uint32_t n1 = 0;             // bases in g1_all
+  // shard: variables [lo, lo+ma) of a/b queries, [l_lo, l_lo+ml) of the witness part, bit-reversed
+  // h positions [h_lo, h_lo+hn); alpha/beta/delta terms on shard 0 only
+  uint32_t lo = 0, ma = 0, l_lo = 0, ml = 0, h_lo = 0, hn = 0, with_vk = 1;
   MsmBases<G1> g1_all;         // [a_query | b_g1_query | l_query | alpha_1 beta_1 delta_1]
   MsmBases<G1> h;              // h_query, bit-reversed order, padded to n
   MsmBases<G2> g2;             // [b_g2_query | beta_2 delta_2]
@@ -121,7 +127,7 @@ struct PkImpl {
   DevBuf<FrEl> ea, eb, ec, z, scal_a, scal_c, hc, tail;
   DevBuf<G1::Xyzz> g1_out;     // A, C_z, C_h
   DevBuf<G2::Xyzz> g2_out;     // B
-  uint32_t* h_out = nullptr;   // pinned: 3 G1 XYZZ + 1 G2 XYZZ
+  uint32_t* h_out = nullptr;   // pinned: 3 G1 XYZZ + 1 G2 XYZZ = B2Z_PARTIAL_BYTES
   cudaEvent_t ev_z = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
@@ -230,18 +236,22 @@ void fixed_base_entry(Ctx& c, const uint64_t* scalars, uint64_t n, uint64_t* out
   std::memcpy(out_inf, words.data(), (n + 7) / 8);
 }
 
-void prove_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
-                  const uint64_t s[4], uint8_t proof_out[192]) {
+constexpr size_t kG1Bytes = sizeof(G1::Xyzz), kG2Bytes = sizeof(G2::Xyzz);
+constexpr size_t kPartialBytes = 3 * kG1Bytes + kG2Bytes;   // A | C_z | C_h | B
+static_assert(kPartialBytes == B2Z_PARTIAL_BYTES, "header constant out of sync");
+
+// GPU part of a proof on this key (a whole key or one shard of it): leaves the XYZZ partial
+// sums A, C_z, C_h (G1) and B (G2) in partial_out (host memory).
+void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
+                          const uint64_t s[4], uint8_t* partial_out) {
   cudaStream_t st = c.stream;
-  const uint32_t m = (uint32_t)pk.m, l = (uint32_t)pk.l;
   // host-side scalars: r, s, r*s as canonical integers
   const FrEl r_m = Fr::reduce(fr_load_host(r)), s_m = Fr::reduce(fr_load_host(s));
   ScalarPrep sp;
   sp.z = d_z;
   sp.out_a = pk.scal_a.p;
   sp.out_c = pk.scal_c.p;
-  sp.m = m;
-  sp.l = l;
+  sp.lo = pk.lo; sp.ma = pk.ma; sp.l_lo = pk.l_lo; sp.ml = pk.ml; sp.with_vk = pk.with_vk;
   sp.r = Fr::from_mont(r_m);
   sp.s = Fr::from_mont(s_m);
   sp.rs = Fr::from_mont(Fr::reduce(Fr::mul(r_m, s_m)));
@@ -249,35 +259,59 @@ void prove_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrE
   one_c.l[0] = 1;
   const FrEl tail_h[2] = {one_c, sp.s};                    // B: {beta_2: 1, delta_2: s}
   B2Z_CUDA(cudaMemcpyAsync(pk.tail.p, tail_h, sizeof(tail_h), cudaMemcpyHostToDevice, c.aux[0]));
-  scalar_prep_kernel<<<nblk(pk.n1, 256), 256, 0, c.aux[0]>>>(sp);
-  B2Z_LAUNCHED(&c);
+  if (pk.n1 > 0) {
+    scalar_prep_kernel<<<nblk(pk.n1, 256), 256, 0, c.aux[0]>>>(sp);
+    B2Z_LAUNCHED(&c);
+  }
   B2Z_CUDA(cudaEventRecord(pk.ev_z, c.aux[0]));
   G1::Xyzz* g1o = pk.g1_out.p;
   // A (aux0), B (aux1), C_z (aux2)
   msm_run<G1>(&c, 1, pk.g1_all, pk.scal_a.p, pk.n1, nullptr, g1o + 0, c.aux[0]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], c.aux[0]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], pk.ev_z, 0));
-  msm_run<G2>(&c, 2, pk.g2, pk.scal_a.p, m, pk.tail.p, pk.g2_out.p, c.aux[1]);
+  msm_run<G2>(&c, 2, pk.g2, pk.scal_a.p, pk.ma, pk.tail.p, pk.g2_out.p, c.aux[1]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[1], c.aux[1]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[2], pk.ev_z, 0));
   msm_run<G1>(&c, 3, pk.g1_all, pk.scal_c.p, pk.n1, nullptr, g1o + 1, c.aux[2]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], c.aux[2]));
-  // witness map + C_h on the main stream
+  // witness map (whole domain, every shard) + this shard's slice of C_h on the main stream
   witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);
-  fr_from_mont_device(&c, d_a, pk.hc.p, (size_t)1 << pk.log_n, st);
-  msm_run<G1>(&c, 0, pk.h, pk.hc.p, 1u << pk.log_n, nullptr, g1o + 2, st);
+  fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
+  msm_run<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, g1o + 2, st);
   for (auto& e : pk.ev_done) B2Z_CUDA(cudaStreamWaitEvent(st, e, 0));
-  constexpr size_t kG1 = sizeof(G1::Xyzz), kG2 = sizeof(G2::Xyzz);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out, g1o, 3 * kG1, cudaMemcpyDeviceToHost, st));
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 3 * kG1 / 4, pk.g2_out.p, kG2, cudaMemcpyDeviceToHost, st));
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out, g1o, 3 * kG1Bytes, cudaMemcpyDeviceToHost, st));
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 3 * kG1Bytes / 4, pk.g2_out.p, kG2Bytes, cudaMemcpyDeviceToHost, st));
   B2Z_CUDA(cudaStreamSynchronize(st));
-  // host epilogue: C = C_z + C_h, three normalisations, serialization
-  const host::G1Xyzz A = host::g1_from_device(pk.h_out);
-  const host::G1Xyzz C = host::g1_add(host::g1_from_device(pk.h_out + kG1 / 4), host::g1_from_device(pk.h_out + 2 * kG1 / 4));
-  const host::G2Xyzz B = host::g2_from_device(pk.h_out + 3 * kG1 / 4);
+  std::memcpy(partial_out, pk.h_out, kPartialBytes);
+}
+
+// Host epilogue: sum the partials of all shards, normalise, serialise (host_fq.hpp).
+void combine_partials(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]) {
+  host::G1Xyzz A, C;
+  host::G2Xyzz B;
+  std::memset(&A, 0, sizeof(A));
+  std::memset(&C, 0, sizeof(C));
+  std::memset(&B, 0, sizeof(B));
+  for (uint32_t k = 0; k < world; k++) {
+    uint32_t w[kPartialBytes / 4];
+    std::memcpy(w, partials + (size_t)k * kPartialBytes, kPartialBytes);
+    A = host::g1_add(A, host::g1_from_device(w));
+    C = host::g1_add(C, host::g1_from_device(w + kG1Bytes / 4));
+    C = host::g1_add(C, host::g1_from_device(w + 2 * kG1Bytes / 4));
+    B = host::g2_add(B, host::g2_from_device(w + 3 * kG1Bytes / 4));
+  }
   host::g1_serialize(proof_out, A);
   host::g2_serialize(proof_out + 48, B);
   host::g1_serialize(proof_out + 144, C);
+}
+
+void prove_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
+                  const uint64_t s[4], uint8_t proof_out[192]) {
+  B2Z_REQUIRE(pk.with_vk && pk.ma == pk.m && pk.hn == (1u << pk.log_n), B2Z_EINVAL,
+              "b2z_groth16_prove needs a whole key; use b2z_groth16_prove_partial + b2z_groth16_combine on shards");
+  uint8_t partial[kPartialBytes];
+  prove_partial_device(c, pk, d_a, d_b, d_c, d_z, r, s, partial);
+  combine_partials(partial, 1, proof_out);
 }
 
 }  // namespace
@@ -311,10 +345,11 @@ b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t
   return guarded(ctx, [&](Ctx& c) { fixed_base_entry<G2>(c, scalars, n, out_points, out_inf); });
 }
 
-b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
+b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank, uint32_t world, b2z_pk** out) {
   if (out) *out = nullptr;
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(d != nullptr && out != nullptr, B2Z_EINVAL, "b2z_pk_upload: NULL argument");
+    B2Z_REQUIRE(world >= 1 && rank < world, B2Z_EINVAL, "b2z_pk_upload_shard: need rank < world");
     B2Z_REQUIRE(d->log_domain <= 32, B2Z_ESIZE, "b2z_pk_upload: domain larger than 2^32");
     B2Z_REQUIRE(d->log_domain <= 26, B2Z_ENOMEM, "b2z_pk_upload: domain does not fit this build's single-GPU plan");
     B2Z_REQUIRE(d->num_instance >= 1 && d->num_variables >= d->num_instance, B2Z_EINVAL,
@@ -329,21 +364,41 @@ b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
     P.log_n = d->log_domain;
     P.m = m;
     P.l = l;
-    P.n1 = (uint32_t)(3 * m - l + 3);
+    // contiguous shards: variables [m rank / world, m (rank+1) / world), same fraction of the h positions
+    const uint64_t lo = m * rank / world, hi = m * (rank + 1) / world;
+    const uint64_t l_lo = lo > l ? lo : l, l_hi = hi > l ? hi : l;      // witness variables in the slice
+    const uint64_t h_lo = n * rank / world, h_hi = n * (rank + 1) / world;
+    P.lo = (uint32_t)lo; P.ma = (uint32_t)(hi - lo);
+    P.l_lo = (uint32_t)l_lo; P.ml = (uint32_t)(l_hi - l_lo);
+    P.h_lo = (uint32_t)h_lo; P.hn = (uint32_t)(h_hi - h_lo);
+    P.with_vk = rank == 0 ? 1u : 0u;
+    P.n1 = 2 * P.ma + P.ml + (P.with_vk ? 3 : 0);
     cudaStream_t st = c.stream;
     size_t free_b = 0, total_b = 0;
     B2Z_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const bool pre = pk_precompute_bytes(d) < free_b / 2;
+    const bool pre = pk_precompute_bytes(d) / world < free_b / 2;
     {
       // G1: [a | b1 | l | alpha beta delta]
-      DevBuf<G1::Affine> dpts(P.n1);
-      std::vector<uint32_t> words((P.n1 + 31) / 32, 0u);
-      stage_points<G1::Affine>(dpts.p, words, 0, d->a_query, d->a_inf, m, st);
-      stage_points<G1::Affine>(dpts.p, words, m, d->b_g1_query, d->b_g1_inf, m, st);
-      stage_points<G1::Affine>(dpts.p, words, 2 * m, d->l_query, d->l_inf, m - l, st);
-      stage_points<G1::Affine>(dpts.p, words, 3 * m - l, d->alpha_g1, nullptr, 1, st);
-      stage_points<G1::Affine>(dpts.p, words, 3 * m - l + 1, d->beta_g1, nullptr, 1, st);
-      stage_points<G1::Affine>(dpts.p, words, 3 * m - l + 2, d->delta_g1, nullptr, 1, st);
+      DevBuf<G1::Affine> dpts(P.n1 ? P.n1 : 1);
+      std::vector<uint32_t> words((P.n1 + 31) / 32 + 1, 0u);
+      auto sub_inf = [](const uint8_t* inf, uint64_t from, uint64_t count, std::vector<uint8_t>& tmp) -> const uint8_t* {
+        if (inf == nullptr) return nullptr;
+        tmp.assign((count + 7) / 8 + 1, 0);
+        for (uint64_t i = 0; i < count; i++)
+          if ((inf[(from + i) >> 3] >> ((from + i) & 7)) & 1) tmp[i >> 3] |= (uint8_t)(1u << (i & 7));
+        return tmp.data();
+      };
+      std::vector<uint8_t> t0, t1, t2;
+      stage_points<G1::Affine>(dpts.p, words, 0, d->a_query + 12 * lo, sub_inf(d->a_inf, lo, P.ma, t0), P.ma, st);
+      stage_points<G1::Affine>(dpts.p, words, P.ma, d->b_g1_query + 12 * lo, sub_inf(d->b_g1_inf, lo, P.ma, t1), P.ma, st);
+      stage_points<G1::Affine>(dpts.p, words, 2 * (uint64_t)P.ma, d->l_query ? d->l_query + 12 * (l_lo - l) : nullptr,
+                               sub_inf(d->l_inf, l_lo - l, P.ml, t2), P.ml, st);
+      if (P.with_vk) {
+        const uint64_t at = 2 * (uint64_t)P.ma + P.ml;
+        stage_points<G1::Affine>(dpts.p, words, at, d->alpha_g1, nullptr, 1, st);
+        stage_points<G1::Affine>(dpts.p, words, at + 1, d->beta_g1, nullptr, 1, st);
+        stage_points<G1::Affine>(dpts.p, words, at + 2, d->delta_g1, nullptr, 1, st);
+      }
       DevBuf<uint32_t> dinf(words.size());
       B2Z_CUDA(cudaMemcpyAsync(dinf.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice, st));
       msm_bases_build<G1>(&c, P.g1_all, dpts.p, dinf.p, P.n1, pre, 0, st);
@@ -351,21 +406,31 @@ b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
     }
     {
       // G2: [b2 | beta_2 delta_2]
-      const uint32_t n2 = (uint32_t)(m + 2);
-      DevBuf<G2::Affine> dpts(n2);
-      std::vector<uint32_t> words((n2 + 31) / 32, 0u);
-      stage_points<G2::Affine>(dpts.p, words, 0, d->b_g2_query, d->b_g2_inf, m, st);
-      stage_points<G2::Affine>(dpts.p, words, m, d->beta_g2, nullptr, 1, st);
-      stage_points<G2::Affine>(dpts.p, words, m + 1, d->delta_g2, nullptr, 1, st);
+      const uint32_t n2 = P.ma + (P.with_vk ? 2 : 0);
+      DevBuf<G2::Affine> dpts(n2 ? n2 : 1);
+      std::vector<uint32_t> words((n2 + 31) / 32 + 1, 0u);
+      std::vector<uint8_t> t0;
+      const uint8_t* inf = nullptr;
+      if (d->b_g2_inf != nullptr) {
+        t0.assign((P.ma + 7) / 8 + 1, 0);
+        for (uint64_t i = 0; i < P.ma; i++)
+          if ((d->b_g2_inf[(lo + i) >> 3] >> ((lo + i) & 7)) & 1) t0[i >> 3] |= (uint8_t)(1u << (i & 7));
+        inf = t0.data();
+      }
+      stage_points<G2::Affine>(dpts.p, words, 0, d->b_g2_query + 24 * lo, inf, P.ma, st);
+      if (P.with_vk) {
+        stage_points<G2::Affine>(dpts.p, words, P.ma, d->beta_g2, nullptr, 1, st);
+        stage_points<G2::Affine>(dpts.p, words, (uint64_t)P.ma + 1, d->delta_g2, nullptr, 1, st);
+      }
       DevBuf<uint32_t> dinf(words.size());
       B2Z_CUDA(cudaMemcpyAsync(dinf.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice, st));
       msm_bases_build<G2>(&c, P.g2, dpts.p, dinf.p, n2, pre, 0, st);
       B2Z_CUDA(cudaStreamSynchronize(st));
     }
     {
-      // h_query in bit-reversed order, padded to n with a flagged identity
+      // h_query in bit-reversed order, padded to n with a flagged identity; keep positions [h_lo, h_hi)
       DevBuf<G1::Affine> src(n), dst(n);
-      DevBuf<uint32_t> src_inf, flags(n), words((n + 31) / 32);
+      DevBuf<uint32_t> src_inf, flags(n), words((P.hn + 31) / 32 + 1);
       if (n > 1) B2Z_CUDA(cudaMemcpyAsync(src.p, d->h_query, (n - 1) * sizeof(G1::Affine), cudaMemcpyHostToDevice, st));
       std::vector<uint32_t> hw;
       if (d->h_inf != nullptr && n > 1) {
@@ -377,19 +442,45 @@ b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
       permute_bitrev_g1_kernel<<<nblk(n, 256), 256, 0, st>>>(src.p, src_inf.p, (uint32_t)(n - 1), P.log_n, dst.p,
                                                              flags.p);
       B2Z_LAUNCHED(&c);
-      pack_flags_kernel2<<<nblk((n + 31) / 32, 128), 128, 0, st>>>(flags.p, (uint32_t)n, words.p);
+      pack_flags_kernel2<<<nblk((P.hn + 31) / 32 + 1, 128), 128, 0, st>>>(flags.p + h_lo, P.hn, words.p);
       B2Z_LAUNCHED(&c);
-      msm_bases_build<G1>(&c, P.h, dst.p, words.p, (uint32_t)n, pre, 0, st);
+      msm_bases_build<G1>(&c, P.h, dst.p + h_lo, words.p, P.hn, pre, 0, st);
       B2Z_CUDA(cudaStreamSynchronize(st));
     }
-    P.ea.alloc(n); P.eb.alloc(n); P.ec.alloc(n); P.hc.alloc(n);
-    P.z.alloc(m); P.scal_a.alloc(P.n1); P.scal_c.alloc(P.n1); P.tail.alloc(2);
+    P.ea.alloc(n); P.eb.alloc(n); P.ec.alloc(n); P.hc.alloc(P.hn ? P.hn : 1);
+    P.z.alloc(m); P.scal_a.alloc(P.n1 ? P.n1 : 1); P.scal_c.alloc(P.n1 ? P.n1 : 1); P.tail.alloc(2);
     P.g1_out.alloc(3); P.g2_out.alloc(1);
-    B2Z_CUDA(cudaMallocHost(&P.h_out, 3 * sizeof(G1::Xyzz) + sizeof(G2::Xyzz)));
+    B2Z_CUDA(cudaMallocHost(&P.h_out, kPartialBytes));
     B2Z_CUDA(cudaEventCreateWithFlags(&P.ev_z, cudaEventDisableTiming));
     for (auto& e : P.ev_done) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = pk.release();
   });
+}
+
+b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
+  return b2z_pk_upload_shard(ctx, d, 0, 1, out);
+}
+
+b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk_c, const uint64_t* a_evals, const uint64_t* b_evals,
+                                     const uint64_t* c_evals, const uint64_t* z, const uint64_t r[4],
+                                     const uint64_t s[4], uint8_t* partial_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk_c && a_evals && b_evals && c_evals && z && r && s && partial_out, B2Z_EINVAL,
+                "b2z_groth16_prove_partial: NULL argument");
+    PkImpl& P = const_cast<b2z_pk*>(pk_c)->impl;
+    const size_t n = (size_t)1 << P.log_n;
+    B2Z_CUDA(cudaMemcpyAsync(P.z.p, z, P.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaMemcpyAsync(P.ea.p, a_evals, n * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
+    B2Z_CUDA(cudaMemcpyAsync(P.eb.p, b_evals, n * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
+    B2Z_CUDA(cudaMemcpyAsync(P.ec.p, c_evals, n * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
+    prove_partial_device(c, P, P.ea.p, P.eb.p, P.ec.p, P.z.p, r, s, partial_out);
+  });
+}
+
+b2z_status b2z_groth16_combine(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]) {
+  if (partials == nullptr || proof_out == nullptr || world == 0) return B2Z_EINVAL;
+  combine_partials(partials, world, proof_out);
+  return B2Z_OK;
 }
 
 void b2z_pk_free(b2z_ctx* ctx, b2z_pk* pk) {

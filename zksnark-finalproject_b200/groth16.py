@@ -245,8 +245,9 @@ class ProvingKey:
         self._ctx = None
         self._handle = None
 
-    def upload(self, ctx):
-        """b2z_pk_upload: copies the key to the device (once per circuit)."""
+    def upload(self, ctx, rank=0, world=1):
+        """b2z_pk_upload / b2z_pk_upload_shard: copies the key (or this rank's point shard of
+        it) to the device, once per circuit."""
         if self._handle is not None:
             return self
         keep = []
@@ -273,8 +274,9 @@ class ProvingKey:
         d.alpha_g1, d.beta_g1, d.delta_g1 = p(self.alpha_g1), p(self.beta_g1), p(self.delta_g1)
         d.beta_g2, d.delta_g2 = p(self.beta_g2), p(self.delta_g2)
         h = ctypes.c_void_p()
-        ctx.check(ctx._lib.b2z_pk_upload(ctx.handle, ctypes.byref(d), ctypes.byref(h)))
+        ctx.check(ctx._lib.b2z_pk_upload_shard(ctx.handle, ctypes.byref(d), int(rank), int(world), ctypes.byref(h)))
         self._ctx, self._handle = ctx, h
+        self.shard = (int(rank), int(world))
         return self
 
     def free(self):
@@ -387,6 +389,47 @@ class Groth16:
         ctx.check(ctx._lib.b2z_groth16_prove(ctx.handle, pk._handle, _ptr(a), _ptr(b), _ptr(c), _ptr(z),
                                              _ptr(rs[0:1]), _ptr(rs[1:2]), _ptr(out)))
         return out.tobytes()
+
+    @staticmethod
+    def create_proof_partial(ctx, pk, a, b, c, full_assignment, r, s):
+        """This rank's share of a point-sharded proof (pk uploaded with upload(ctx, rank, world)):
+        B2Z_PARTIAL_BYTES of XYZZ partial sums.  Every rank passes the same full inputs."""
+        a, b, c, z = _fr_array(a), _fr_array(b), _fr_array(c), _fr_array(full_assignment)
+        if a.shape[0] != pk.domain_size or z.shape[0] != pk.num_variables:
+            raise ValueError("inputs do not match the key")
+        rs = codec.fr_to_mont_limbs([r, s])
+        out = np.zeros(_ffi.PARTIAL_BYTES, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_groth16_prove_partial(ctx.handle, pk._handle, _ptr(a), _ptr(b), _ptr(c), _ptr(z),
+                                                     _ptr(rs[0:1]), _ptr(rs[1:2]), _ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
+    def combine(partials):
+        """b2z_groth16_combine: host-only sum of the shards' partials (rank order) -> 192 proof bytes."""
+        buf = np.frombuffer(b"".join(partials), dtype=np.uint8).copy()
+        if buf.size != len(partials) * _ffi.PARTIAL_BYTES:
+            raise ValueError("each partial must be %d bytes" % _ffi.PARTIAL_BYTES)
+        out = np.zeros(192, dtype=np.uint8)
+        st = _ffi.lib().b2z_groth16_combine(_ptr(buf), len(partials), _ptr(out))
+        if st != _ffi.B2Z_OK:
+            raise _ffi.B2zError(st, "b2z_groth16_combine failed")
+        return out.tobytes()
+
+    @staticmethod
+    def create_proof_sharded(ctx, pk, a, b, c, full_assignment, r, s, group=None):
+        """One proof computed by all ranks of a torch.distributed group (one process per GPU):
+        partial sums on every rank, one all_gather of 960 bytes per rank, host combine.
+        Returns the proof bytes on every rank."""
+        import torch
+        import torch.distributed as dist
+        mine = Groth16.create_proof_partial(ctx, pk, a, b, c, full_assignment, r, s)
+        world = dist.get_world_size(group)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        return Groth16.combine([bytes(x.cpu().numpy().tobytes()) for x in parts])
 
     @staticmethod
     def create_random_proof_with_reduction(ctx, pk, matrices, num_constraints, full_assignment_ints, rng):
