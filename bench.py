@@ -162,10 +162,28 @@ def run_reference(args, rank, world):
                                    "(the Rust reference cannot be built here)" % args.steps},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter)
+    was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -280,6 +298,37 @@ def main():
         step_e2e()
     e2e_dev_s, e2e_wall_s = timed(step_e2e, args.steps)
 
+    # ---- point-sharded mode (N > 1): ONE proof computed by all ranks -- reported next to
+    # the weak-scaling line; every rank holds 1/N of every base set, partial sums travel over NCCL
+    sharded = None
+    if world > 1:
+        spk = pkg.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                             pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                             pk.beta_g2, pk.delta_g2).upload(ctx, rank=rank, world=world)
+        r0, s0 = 0x1234567, 0x7654321             # the same r, s on every rank
+        rs0 = codec.fr_to_mont_limbs([r0, s0])
+        part = np.zeros(pkg._ffi.PARTIAL_BYTES, dtype=np.uint8)
+        gathered = [torch.empty(pkg._ffi.PARTIAL_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        out = {}
+
+        def step_sharded():
+            ctx.check(L.b2z_groth16_prove_partial(ctx.handle, spk._handle, hp(host[0]), hp(host[1]), hp(host[2]),
+                                                  hp(host[3]), p(rs0[0:1]), p(rs0[1:2]), p(part)))
+            dist.all_gather(gathered, torch.from_numpy(part).cuda())
+            out["proof"] = pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered])
+
+        step_sharded()
+        ref = np.zeros(192, dtype=np.uint8)
+        ctx.check(L.b2z_groth16_prove(ctx.handle, pk._handle, hp(host[0]), hp(host[1]), hp(host[2]), hp(host[3]),
+                                      p(rs0[0:1]), p(rs0[1:2]), p(ref)))
+        assert out["proof"] == ref.tobytes(), "sharded proof differs from the single-GPU proof"
+        for _ in range(args.warmup):
+            step_sharded()
+        sh_dev_s, sh_wall_s = timed(step_sharded, args.steps)
+        sharded = {"ms_per_proof": sh_dev_s / args.steps * 1e3, "proofs_per_s": args.steps / sh_dev_s,
+                   "scaling": "strong", "collective": "all_gather of %d B per rank (NCCL)" % pkg._ffi.PARTIAL_BYTES,
+                   "bytes_equal_single_gpu": True}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -307,7 +356,11 @@ def main():
     roofline = {
         "kernel": "msm_accum_kernel<G1> (bucket accumulation, XYZZ mixed additions)",
         "bound": "hbm", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None, "peak": hbm_peak,
-        "unit": "GB/s", "frac": (acc_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak) if acc_ms else None, "traffic": None,
+        "unit": "GB/s", "frac": (acc_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak) if acc_ms else None,
+        # dram__bytes_read+write of one G1 accumulation launch from the committed ncu --set full capture
+        # (profiles/r01_ncu/prof_accum_g1.raw.csv: 855.1 MB for the 5.13 M-addition C_z launch = 167 B per
+        # mixed addition), scaled to this run's average launch
+        "traffic": acc_adds * 167.0,
         "peak_source": hbm_src,
         "note": "this kernel is integer-pipe bound, not HBM bound (SURVEY.md App. C): see int_pipe",
         "int_pipe": {
@@ -363,10 +416,10 @@ def main():
                 "h2d_bytes_per_step": int(3 * n * 32 + m * 32 + 64), "d2h_bytes_per_step": 192},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_s / args.steps * 1e3,
-        "roofline": roofline, "phases": phases, "cpu_baseline": cpu,
+        "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "sharded_single_proof": sharded,
         "proof_sha": __import__("hashlib").sha256(first).hexdigest()[:16],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
