@@ -44,16 +44,30 @@ WORKLOADS = {
     "c2": "matrix-multiplication 16x16 with Poseidon-shaped hashes (BASELINE configs[1]): "
           "109955 constraints, domain 2^17",
     "m8": "matrix-multiplication 8x8 (development size): domain 2^15",
+    "c5": "matrix-multiplication 64x64 with Poseidon-shaped hashes (BASELINE configs[4] shape): "
+          "2152451 constraints, domain 2^22",
 }
 
 
+class Instance:
+    """What the prover consumes: constraint matrices (CSR) + assignment."""
+
+    def __init__(self, cm, z):
+        self.cm, self.z = cm, z
+        self.num_constraints, self.num_instance = cm.num_constraints, cm.num_instance_variables
+        self.num_variables, self.domain_size = cm.num_variables, cm.domain_size
+
+
 def build_instance(name):
-    circuits = importlib.import_module(PKG + ".circuits")
+    pkg = importlib.import_module(PKG)
     if name == "c1":
-        return circuits.fibonacci_circuit(0, 1, 1000)
-    n = {"c2": 16, "m8": 8}[name]
+        inst = importlib.import_module(PKG + ".circuits").fibonacci_circuit(0, 1, 1000)
+        cm = pkg.ConstraintMatrices.from_rows(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c)
+        return Instance(cm, inst.z)
+    n = {"c2": 16, "m8": 8, "c5": 64}[name]
     ones = [[1] * n for _ in range(n)]                 # bench/matrix.py:10-11 posts all-ones matrices
-    return circuits.matrix_circuit(ones, ones)
+    cm, z = importlib.import_module(PKG + ".circuits_fast").matrix_circuit_fast(ones, ones)
+    return Instance(cm, z)
 
 
 class ClockSampler:
@@ -125,12 +139,17 @@ def run_reference(args, rank, world):
     # else (no GPU on this host) by the Python oracle -- either way outside the timed region
     try:
         ctx = pkg.Context(0)
-        pk, _ = pkg.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+        pk, _ = pkg.Groth16.generate_parameters_with_qap(ctx, inst.cm, inst.num_constraints, inst.num_instance,
                                                          inst.num_variables, *toxic_waste())
+        a, b, c = pkg.LibsnarkReduction.constraint_evaluations_device(ctx, inst.cm, codec.fr_to_mont_limbs(inst.z))
         ctx.close()
     except Exception:
         from oracle import groth16 as OG
-        opk = OG.setup(OG.R1CS(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c), toxic=toxic_waste())
+        ra, rb, rc = inst.cm.rows()
+        a, b, c = pkg.LibsnarkReduction.constraint_evaluations((ra, rb, rc), inst.num_instance, inst.num_constraints,
+                                                               inst.z)
+        opk = OG.setup(OG.R1CS(inst.num_instance, inst.num_variables - inst.num_instance, ra, rb, rc),
+                       toxic=toxic_waste())
         q1, q2 = codec.g1_to_limbs, codec.g2_to_limbs
         pk = pkg.ProvingKey(opk.num_variables, opk.num_instance, opk.domain_size, q1(opk.a_query), q1(opk.b_g1_query),
                             q2(opk.b_g2_query), q1(opk.h_query), q1(opk.l_query), q1([opk.alpha_g1])[0][0],
@@ -139,7 +158,6 @@ def run_reference(args, rank, world):
     cpu_oracle, cpk = cpu_prove_setup(pkg, inst, pk)
     cores = cpu_oracle.hardware_threads()
     cpu_oracle.set_threads(cores)
-    a, b, c = pkg.LibsnarkReduction.constraint_evaluations(inst.matrices, inst.num_instance, inst.num_constraints, inst.z)
     z = codec.fr_to_mont_limbs(inst.z)
     rnd = random.Random(SEED ^ 1)
     rs = codec.fr_to_mont_limbs([rnd.randrange(R_MOD), rnd.randrange(R_MOD)])
@@ -220,11 +238,12 @@ def main():
 
     # ---- workload (outside the timed region)
     inst = build_instance(args.workload)
-    pk, vk = pkg.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+    pk, vk = pkg.Groth16.generate_parameters_with_qap(ctx, inst.cm, inst.num_constraints, inst.num_instance,
                                                       inst.num_variables, *toxic_waste())
     pk.upload(ctx)
-    a, b, c = pkg.LibsnarkReduction.constraint_evaluations(inst.matrices, inst.num_instance, inst.num_constraints, inst.z)
+    inst.cm.upload(ctx)
     z = codec.fr_to_mont_limbs(inst.z)
+    a, b, c = pkg.LibsnarkReduction.constraint_evaluations_device(ctx, inst.cm, z)
     n, m = inst.domain_size, inst.num_variables
     rnd = random.Random(SEED ^ 1 ^ (rank << 8))      # each rank proves with its own r, s
     r, s = rnd.randrange(R_MOD), rnd.randrange(R_MOD)
@@ -248,8 +267,10 @@ def main():
         ctx.check(st)
 
     def step_e2e():
-        st = L.b2z_groth16_prove(ctx.handle, pk._handle, hp(host[0]), hp(host[1]), hp(host[2]), hp(host[3]),
-                                 p(rs[0:1]), p(rs[1:2]), p(proof))
+        # the call a user of the reference makes: assignment in host memory -> 192 proof bytes; the
+        # constraint rows are evaluated on the GPU from the uploaded matrices (b2z_groth16_prove_r1cs)
+        st = L.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, inst.cm._handle, hp(host[3]), p(rs[0:1]), p(rs[1:2]),
+                                      p(proof))
         ctx.check(st)
 
     def barrier():
@@ -413,7 +434,8 @@ def main():
                                    (key_bytes / 1e6, (3 * n + m) * 32 / 1e6)},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "proofs/s", "ms_per_step": e2e_dev_s / args.steps * 1e3,
-                "h2d_bytes_per_step": int(3 * n * 32 + m * 32 + 64), "d2h_bytes_per_step": 192},
+                "h2d_bytes_per_step": int(m * 32 + 64), "d2h_bytes_per_step": 960,
+                "call": "b2z_groth16_prove_r1cs (row evaluation + witness map + 4 MSMs + host epilogue)"},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_s / args.steps * 1e3,
         "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "sharded_single_proof": sharded,

@@ -120,6 +120,31 @@ B2Z_API b2z_status b2z_groth16_prove(b2z_ctx* ctx, const b2z_pk* pk, const uint6
                              const uint64_t* z, const uint64_t r[4], const uint64_t s[4],
                              uint8_t proof_out[192]);
 
+/* ---- constraint matrices on the device (ark_relations ConstraintMatrices) ---------------------
+ * The `evaluate_constraint` loop of LibsnarkReduction::witness_map_from_matrices: upload the three
+ * R1CS matrices once per circuit as CSR (row_ptr: num_constraints + 1 offsets; cols: variable
+ * indices into z = instance || witness; coeffs: Fr Montgomery limbs, 4 per entry), then each proof
+ * sends only the assignment z.  b2z_witness_map_from_matrices is the whole arkworks function;
+ * b2z_groth16_prove_r1cs is b2z_groth16_prove with the row evaluation done on the GPU.          */
+typedef struct b2z_r1cs b2z_r1cs;
+B2Z_API b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_instance,
+                                   uint64_t num_variables,
+                                   const uint64_t* a_row_ptr, const uint32_t* a_cols, const uint64_t* a_coeffs,
+                                   const uint64_t* b_row_ptr, const uint32_t* b_cols, const uint64_t* b_coeffs,
+                                   const uint64_t* c_row_ptr, const uint32_t* c_cols, const uint64_t* c_coeffs,
+                                   b2z_r1cs** out);
+B2Z_API void b2z_r1cs_free(b2z_ctx* ctx, b2z_r1cs* r1cs);
+B2Z_API b2z_status b2z_r1cs_eval(b2z_ctx* ctx, b2z_r1cs* r1cs, const uint64_t* z, uint64_t* a_out, uint64_t* b_out,
+                                 uint64_t* c_out);
+/* y = M x over Fr for a one-off CSR matrix (host buffers; x, coeffs, y Montgomery limbs).  Key
+ * generation uses it for the QAP evaluation at tau (the transposed matrices times the Lagrange
+ * coefficients: LibsnarkReduction::instance_map_with_evaluation).                                */
+B2Z_API b2z_status b2z_spmv_fr(b2z_ctx* ctx, uint64_t nrows, uint64_t ncols, const uint64_t* row_ptr,
+                               const uint32_t* cols, const uint64_t* coeffs, const uint64_t* x, uint64_t* y_out);
+B2Z_API b2z_status b2z_witness_map_from_matrices(b2z_ctx* ctx, b2z_r1cs* r1cs, const uint64_t* z, uint64_t* h_out);
+B2Z_API b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r1cs, const uint64_t* z,
+                                          const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
 /* ---- point-sharded proving across the GPUs of one box ------------------------------------
  * An MSM is a sum over independent (scalar, point) pairs, so a proof shards by points
  * (SURVEY.md 8(e)): rank k of `world` keeps variables [m k/world, m (k+1)/world) of the

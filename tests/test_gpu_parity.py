@@ -339,6 +339,42 @@ def test_prove_matrix_16x16_full_size(b2z, ctx, codec, cpu_oracle, circuits):
     _setup_prove_verify(b2z, ctx, codec, cpu_oracle, inst, 4)
 
 
+# ------------------------------------------------------------------------------- constraint matrices on the device
+def test_r1cs_rows_witness_map_and_prove_on_device(b2z, ctx, codec, circuits):
+    """Row f1: the evaluate_constraint loop, witness_map_from_matrices and the whole prove with
+    only z crossing PCIe -- each equal to the host-row path / the oracle."""
+    import importlib
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    A = [[(3 * i + j + 1) for j in range(4)] for i in range(4)]
+    B = [[(i * j + 2) for j in range(4)] for i in range(4)]
+    cm, z_int = fast.matrix_circuit_fast(A, B)
+    inst = circuits.matrix_circuit(A, B)
+    assert z_int == inst.z
+    z = codec.fr_to_mont_limbs(z_int)
+    a_h, b_h, c_h = b2z.LibsnarkReduction.constraint_evaluations(inst.matrices, inst.num_instance,
+                                                                 inst.num_constraints, inst.z)
+    a_d, b_d, c_d = b2z.LibsnarkReduction.constraint_evaluations_device(ctx, cm, z)
+    assert np.array_equal(a_d, a_h) and np.array_equal(b_d, b_h) and np.array_equal(c_d, c_h)
+    h = b2z.LibsnarkReduction.witness_map_from_matrices(ctx, cm, cm.num_instance_variables, cm.num_constraints, z)
+    want = OG.witness_map_from_evals(*(codec.fr_from_mont_limbs(x) for x in (a_h, b_h, c_h)))
+    assert codec.fr_from_mont_limbs(h) == want
+    rnd = random.Random(77)
+    toxic = [rnd.randrange(1, R) for _ in range(5)]
+    pk_rows, _ = b2z.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+                                                           inst.num_variables, *toxic)
+    pk_dev, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                          cm.num_variables, *toxic)
+    for f in b2z.ProvingKey.FIELDS:        # key generation through the GPU SpMV gives the same key
+        assert np.array_equal(getattr(pk_rows, f)[0], getattr(pk_dev, f)[0]), f
+    r, s = rnd.randrange(R), rnd.randrange(R)
+    p1 = b2z.Groth16.create_proof_with_reduction(ctx, pk_dev, a_h, b_h, c_h, z, r, s)
+    p2 = b2z.Groth16.create_proof_with_matrices(ctx, pk_dev, cm, z, r, s)
+    assert p1 == p2
+    cm.free()
+    pk_rows.free()
+    pk_dev.free()
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_prove_point_sharded_equals_whole_key(b2z, ctx, codec, circuits, world):
     """the shards of one key (here all on one GPU, one after the other) produce

@@ -154,6 +154,20 @@ def test_circuit_shapes(circuits):
     assert bools > 0.6 * len(p.z)
 
 
+@pytest.mark.parametrize("n", [2, 3])
+def test_vectorised_matrix_circuit_equals_symbolic_builder(b2z, circuits, n):
+    import importlib
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    A = [[(3 * i + j + 1) for j in range(n)] for i in range(n)]
+    B = [[(i * j + 2) for j in range(n)] for i in range(n)]
+    slow = circuits.matrix_circuit(A, B)
+    cm, z = fast.matrix_circuit_fast(A, B)
+    assert z == slow.z and cm.num_constraints == slow.num_constraints and cm.num_variables == slow.num_variables
+    for got, want in zip(cm.rows(), (slow.a, slow.b, slow.c)):
+        assert all(sorted(x) == sorted(y) for x, y in zip(got, want))
+    assert cm.domain_size == slow.domain_size
+
+
 def test_domain_too_large_maps_to_polynomial_degree_too_large(b2z):
     with pytest.raises(b2z.PolynomialDegreeTooLarge):
         b2z.Radix2EvaluationDomain(None, (1 << 32) + 1)

@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""BASELINE config 5 shape on ONE GPU (and the CPU baseline once): the 64x64 matrix-multiplication
+circuit, 2 152 451 constraints, domain 2^22.  Builds the system with the vectorised builder,
+generates a valid key on the GPU, proves, checks the proof with the pairing verifier of the oracle
+and (optionally) against the C++ CPU restatement.  Prints one JSON line.
+
+    python tools/run_c5.py [--size 64] [--cpu] [--steps 3]
+"""
+import argparse, ctypes, importlib, json, os, random, sys, time
+import numpy as np
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+b = importlib.import_module("zksnark-finalproject_b200")
+fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+from oracle import bls12_381 as O, groth16 as OG
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=64)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--cpu", action="store_true")
+args = ap.parse_args()
+codec = b.codec
+R = O.R_MOD
+t0 = time.time()
+n = args.size
+cm, z_int = fast.matrix_circuit_fast([[1] * n for _ in range(n)], [[1] * n for _ in range(n)])
+t_build = time.time() - t0
+ctx = b.Context(0)
+rnd = random.Random(0xB2000004)
+toxic = [rnd.randrange(1, R) for _ in range(5)]
+t0 = time.time()
+pk, vk = b.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                cm.num_variables, *toxic)
+t_keygen = time.time() - t0
+t0 = time.time()
+pk.upload(ctx)
+cm.upload(ctx)
+t_upload = time.time() - t0
+z = codec.fr_to_mont_limbs(z_int)
+r, s = rnd.randrange(R), rnd.randrange(R)
+proof = b.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r, s)      # warm-up (twiddle tables, scratch)
+L = ctx._lib
+L.b2z_profile_enable(ctx.handle, 1)
+times = []
+for _ in range(args.steps):
+    t0 = time.perf_counter()
+    p2 = b.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r, s)
+    times.append(time.perf_counter() - t0)
+    assert p2 == proof
+ms = (ctypes.c_double * 8)(); cnt = (ctypes.c_uint64 * 8)(); units = (ctypes.c_uint64 * 8)()
+ctx.check(L.b2z_profile_read(ctx.handle, ms, cnt, units, 1))
+names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "finalize"]
+# pairing check (the reference's acceptance test) with the verifying key made by the same GPU key generation
+class V: pass
+v = V()
+v.alpha_g1 = codec.g1_from_limbs(vk.alpha_g1.reshape(1, -1))[0]
+v.beta_g2, v.gamma_g2, v.delta_g2 = (codec.g2_from_limbs(x.reshape(1, -1))[0] for x in (vk.beta_g2, vk.gamma_g2, vk.delta_g2))
+v.gamma_abc_g1 = codec.g1_from_limbs(*vk.gamma_abc_g1)
+ok = OG.verify(v, z_int[1:cm.num_instance_variables], O.proof_deserialize_compressed(proof))
+out = {"workload": "matrix %dx%d" % (n, n), "num_constraints": cm.num_constraints, "domain": cm.domain_size,
+       "num_variables": cm.num_variables, "build_s": t_build, "keygen_s": t_keygen, "upload_s": t_upload,
+       "prove_ms_e2e_host_z": [t * 1e3 for t in times], "proof_verifies": bool(ok),
+       "phases_ms_per_proof": {nm: ms[i] / args.steps for i, nm in enumerate(names)},
+       "g1_mixed_adds_per_proof": units[3] / args.steps, "g2_mixed_adds_per_proof": units[4] / args.steps}
+if args.cpu:
+    from oracle import cpu_oracle
+    a, bb, c = b.LibsnarkReduction.constraint_evaluations_device(ctx, cm, z)
+    cpk = cpu_oracle.CpuProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                                   pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                                   pk.beta_g2, pk.delta_g2)
+    cores = cpu_oracle.hardware_threads()
+    cpu_oracle.set_threads(cores)
+    rs = codec.fr_to_mont_limbs([r, s])
+    t0 = time.perf_counter()
+    cpu_proof = cpk.prove(a, bb, c, z, rs[0], rs[1])
+    out["cpu_prove_s"] = time.perf_counter() - t0
+    out["cpu_cores"] = cores
+    out["cpu_bytes_equal_gpu"] = cpu_proof == proof
+print(json.dumps(out), flush=True)

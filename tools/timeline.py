@@ -8,14 +8,13 @@ b = importlib.import_module("zksnark-finalproject_b200")
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 ctx = b.Context(0)
 inst = bench.build_instance(name)
-pk, vk = b.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+pk, vk = b.Groth16.generate_parameters_with_qap(ctx, inst.cm, inst.num_constraints, inst.num_instance,
                                                 inst.num_variables, *bench.toxic_waste())
-a, bb, c = b.LibsnarkReduction.constraint_evaluations(inst.matrices, inst.num_instance, inst.num_constraints, inst.z)
 z = b.codec.fr_to_mont_limbs(inst.z)
 for i in range(4):
     if i == 3:
         ctx._lib.b2z_profile_enable(ctx.handle, 1)
-    b.Groth16.create_proof_with_reduction(ctx, pk, a, bb, c, z, 123456789, 987654321)
+    b.Groth16.create_proof_with_matrices(ctx, pk, inst.cm, z, 123456789, 987654321)
 N = 4096
 ph = (ctypes.c_int * N)(); t0 = (ctypes.c_double * N)(); t1 = (ctypes.c_double * N)()
 n = ctx._lib.b2z_profile_spans(ctx.handle, N, ph, t0, t1)

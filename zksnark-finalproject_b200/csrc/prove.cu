@@ -29,6 +29,7 @@
 #include "api_glue.hpp"
 #include "host_fq.hpp"
 #include "msm.hpp"
+#include "prove_internal.hpp"
 
 namespace b2z {
 
@@ -322,6 +323,16 @@ using namespace b2z;
 struct b2z_pk {
   PkImpl impl;
 };
+
+namespace b2z {
+bool pk_matches(const b2z_pk* pk, uint32_t log_n, uint64_t m, uint64_t l) {
+  return pk->impl.log_n == log_n && pk->impl.m == m && pk->impl.l == l;
+}
+void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
+                             const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]) {
+  prove_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, proof_out);
+}
+}  // namespace b2z
 
 extern "C" {
 

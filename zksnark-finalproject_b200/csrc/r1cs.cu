@@ -1,0 +1,222 @@
+// Constraint-row evaluation on the device -- the `evaluate_constraint` loop at the top of
+// ark-groth16's LibsnarkReduction::witness_map_from_matrices:
+//   a[i] = <A_i, z>, b[i] = <B_i, z>, c[i] = <C_i, z>   for i < num_constraints
+//   a[num_constraints + j] = z[j]                       for j < num_instance ; zero elsewhere
+// The matrices are static per circuit: uploaded once as CSR (row offsets, column indices,
+// Montgomery coefficients), then every proof sends only z (32 B per variable) instead of the
+// three evaluation vectors (96 B per domain point).  A gather-bound kernel: one thread per row.
+#include <cstring>
+
+#include "api_glue.hpp"
+#include "msm.hpp"
+#include "prove_internal.hpp"
+
+namespace b2z {
+
+struct CsrDev {
+  DevBuf<uint32_t> row_ptr, cols;
+  DevBuf<FrEl> coeffs;
+};
+
+struct R1csImpl {
+  uint64_t nc = 0, l = 0, m = 0;
+  uint32_t log_n = 0;
+  CsrDev mat[3];
+  DevBuf<FrEl> z, ea, eb, ec;
+};
+
+namespace {
+
+__device__ __forceinline__ FrEl ldg32(const FrEl* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 a = __ldg(q), b = __ldg(q + 1);
+  FrEl r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
+}
+
+// grid.y selects the matrix; out[mat][row]
+__global__ void r1cs_eval_kernel(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ ci0,
+                                 const FrEl* __restrict__ cf0, const uint32_t* __restrict__ rp1,
+                                 const uint32_t* __restrict__ ci1, const FrEl* __restrict__ cf1,
+                                 const uint32_t* __restrict__ rp2, const uint32_t* __restrict__ ci2,
+                                 const FrEl* __restrict__ cf2, const FrEl* __restrict__ z, uint32_t nc, uint32_t l,
+                                 FrEl* a, FrEl* b, FrEl* c) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t which = blockIdx.y;
+  const uint32_t* rp = which == 0 ? rp0 : (which == 1 ? rp1 : rp2);
+  const uint32_t* ci = which == 0 ? ci0 : (which == 1 ? ci1 : ci2);
+  const FrEl* cf = which == 0 ? cf0 : (which == 1 ? cf1 : cf2);
+  FrEl* out = which == 0 ? a : (which == 1 ? b : c);
+  if (row < nc) {
+    FrEl acc = Fr::zero();
+    const uint32_t end = rp[row + 1];
+    for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, Fr::mul(ldg32(cf + k), ldg32(z + ci[k])));   // coeff canonical
+    out[row] = Fr::reduce(acc);
+  } else if (which == 0 && row < nc + l) {
+    out[row] = Fr::reduce(ldg32(z + (row - nc)));
+  }
+}
+
+// y = M x  for a CSR matrix over Fr (x, coefficients canonical Montgomery); one thread per row
+__global__ void spmv_kernel(const uint32_t* __restrict__ rp, const uint32_t* __restrict__ ci,
+                            const FrEl* __restrict__ cf, const FrEl* __restrict__ x, uint32_t nrows, FrEl* y) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  FrEl acc = Fr::zero();
+  const uint32_t end = rp[row + 1];
+  for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, Fr::mul(ldg32(cf + k), ldg32(x + ci[k])));
+  y[row] = Fr::reduce(acc);
+}
+
+void upload_csr(CsrDev& d, const uint64_t* row_ptr, const uint32_t* cols, const uint64_t* coeffs, uint64_t nc,
+                uint64_t m, cudaStream_t st) {
+  B2Z_REQUIRE(row_ptr != nullptr, B2Z_EINVAL, "b2z_r1cs_upload: NULL row_ptr");
+  const uint64_t nnz = row_ptr[nc];
+  B2Z_REQUIRE(row_ptr[0] == 0 && nnz < (1ull << 32), B2Z_EINVAL, "b2z_r1cs_upload: bad row_ptr");
+  B2Z_REQUIRE(nnz == 0 || (cols != nullptr && coeffs != nullptr), B2Z_EINVAL, "b2z_r1cs_upload: NULL entries");
+  std::vector<uint32_t> rp(nc + 1);
+  for (uint64_t i = 0; i <= nc; i++) {
+    B2Z_REQUIRE(i == 0 || row_ptr[i] >= row_ptr[i - 1], B2Z_EINVAL, "b2z_r1cs_upload: row_ptr not monotone");
+    rp[i] = (uint32_t)row_ptr[i];
+  }
+  for (uint64_t k = 0; k < nnz; k++) B2Z_REQUIRE(cols[k] < m, B2Z_EINVAL, "b2z_r1cs_upload: column out of range");
+  d.row_ptr.alloc(nc + 1);
+  d.cols.alloc(nnz ? nnz : 1);
+  d.coeffs.alloc(nnz ? nnz : 1);
+  B2Z_CUDA(cudaMemcpyAsync(d.row_ptr.p, rp.data(), (nc + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (nnz) {
+    B2Z_CUDA(cudaMemcpyAsync(d.cols.p, cols, nnz * 4, cudaMemcpyHostToDevice, st));
+    B2Z_CUDA(cudaMemcpyAsync(d.coeffs.p, coeffs, nnz * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+  }
+  B2Z_CUDA(cudaStreamSynchronize(st));   // rp is a local
+}
+
+void eval_rows(Ctx& c, R1csImpl& R, const FrEl* d_z, FrEl* a, FrEl* b, FrEl* cc, cudaStream_t st) {
+  const size_t n = (size_t)1 << R.log_n;
+  B2Z_CUDA(cudaMemsetAsync(a, 0, n * sizeof(FrEl), st));
+  B2Z_CUDA(cudaMemsetAsync(b, 0, n * sizeof(FrEl), st));
+  B2Z_CUDA(cudaMemsetAsync(cc, 0, n * sizeof(FrEl), st));
+  const uint32_t rows = (uint32_t)(R.nc + R.l);
+  const dim3 grid((rows + 127) / 128, 3);
+  r1cs_eval_kernel<<<grid, 128, 0, st>>>(R.mat[0].row_ptr.p, R.mat[0].cols.p, R.mat[0].coeffs.p, R.mat[1].row_ptr.p,
+                                         R.mat[1].cols.p, R.mat[1].coeffs.p, R.mat[2].row_ptr.p, R.mat[2].cols.p,
+                                         R.mat[2].coeffs.p, d_z, (uint32_t)R.nc, (uint32_t)R.l, a, b, cc);
+  B2Z_LAUNCHED(&c);
+}
+
+}  // namespace
+}  // namespace b2z
+
+using namespace b2z;
+
+struct b2z_r1cs {
+  R1csImpl impl;
+};
+
+extern "C" {
+
+b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_instance, uint64_t num_variables,
+                           const uint64_t* a_row_ptr, const uint32_t* a_cols, const uint64_t* a_coeffs,
+                           const uint64_t* b_row_ptr, const uint32_t* b_cols, const uint64_t* b_coeffs,
+                           const uint64_t* c_row_ptr, const uint32_t* c_cols, const uint64_t* c_coeffs, b2z_r1cs** out) {
+  if (out) *out = nullptr;
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(out != nullptr, B2Z_EINVAL, "b2z_r1cs_upload: NULL out");
+    B2Z_REQUIRE(num_instance >= 1 && num_variables >= num_instance, B2Z_EINVAL, "b2z_r1cs_upload: bad variable counts");
+    uint32_t log_n = 0;
+    while ((1ull << log_n) < num_constraints + num_instance) log_n++;
+    B2Z_REQUIRE(log_n <= 32, B2Z_ESIZE, "b2z_r1cs_upload: domain larger than 2^32 (PolynomialDegreeTooLarge)");
+    B2Z_REQUIRE(log_n <= 28, B2Z_ENOMEM, "b2z_r1cs_upload: domain does not fit this build's single-GPU plan");
+    std::unique_ptr<b2z_r1cs> r(new b2z_r1cs());
+    R1csImpl& R = r->impl;
+    R.nc = num_constraints; R.l = num_instance; R.m = num_variables; R.log_n = log_n;
+    upload_csr(R.mat[0], a_row_ptr, a_cols, a_coeffs, num_constraints, num_variables, c.stream);
+    upload_csr(R.mat[1], b_row_ptr, b_cols, b_coeffs, num_constraints, num_variables, c.stream);
+    upload_csr(R.mat[2], c_row_ptr, c_cols, c_coeffs, num_constraints, num_variables, c.stream);
+    const size_t n = (size_t)1 << log_n;
+    R.z.alloc(num_variables); R.ea.alloc(n); R.eb.alloc(n); R.ec.alloc(n);
+    *out = r.release();
+  });
+}
+
+void b2z_r1cs_free(b2z_ctx* ctx, b2z_r1cs* r) {
+  if (r == nullptr) return;
+  if (ctx != nullptr) {
+    std::lock_guard<std::mutex> lock(ctx->impl.mu);
+    cudaSetDevice(ctx->impl.device);
+    cudaDeviceSynchronize();
+  }
+  delete r;
+}
+
+b2z_status b2z_r1cs_eval(b2z_ctx* ctx, b2z_r1cs* r, const uint64_t* z, uint64_t* a_out, uint64_t* b_out,
+                         uint64_t* c_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(r && z && a_out && b_out && c_out, B2Z_EINVAL, "b2z_r1cs_eval: NULL argument");
+    R1csImpl& R = r->impl;
+    const size_t n = (size_t)1 << R.log_n;
+    cudaStream_t st = c.stream;
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, st);
+    B2Z_CUDA(cudaMemcpyAsync(a_out, R.ea.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaMemcpyAsync(b_out, R.eb.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaMemcpyAsync(c_out, R.ec.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+b2z_status b2z_spmv_fr(b2z_ctx* ctx, uint64_t nrows, uint64_t ncols, const uint64_t* row_ptr, const uint32_t* cols,
+                       const uint64_t* coeffs, const uint64_t* x, uint64_t* y_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(row_ptr && x && y_out, B2Z_EINVAL, "b2z_spmv_fr: NULL argument");
+    B2Z_REQUIRE(nrows < (1ull << 31) && ncols < (1ull << 31), B2Z_ESIZE, "b2z_spmv_fr: matrix too large");
+    CsrDev d;
+    upload_csr(d, row_ptr, cols, coeffs, nrows, ncols, c.stream);
+    DevBuf<FrEl> dx(ncols ? ncols : 1), dy(nrows ? nrows : 1);
+    B2Z_CUDA(cudaMemcpyAsync(dx.p, x, ncols * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
+    if (nrows) {
+      spmv_kernel<<<(uint32_t)((nrows + 127) / 128), 128, 0, c.stream>>>(d.row_ptr.p, d.cols.p, d.coeffs.p, dx.p,
+                                                                        (uint32_t)nrows, dy.p);
+      B2Z_LAUNCHED(&c);
+    }
+    B2Z_CUDA(cudaMemcpyAsync(y_out, dy.p, nrows * sizeof(FrEl), cudaMemcpyDeviceToHost, c.stream));
+    B2Z_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+b2z_status b2z_witness_map_from_matrices(b2z_ctx* ctx, b2z_r1cs* r, const uint64_t* z, uint64_t* h_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(r && z && h_out, B2Z_EINVAL, "b2z_witness_map_from_matrices: NULL argument");
+    R1csImpl& R = r->impl;
+    const size_t n = (size_t)1 << R.log_n;
+    cudaStream_t st = c.stream;
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+    eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, st);
+    witness_map_device(&c, R.ea.p, R.eb.p, R.ec.p, R.log_n, /*natural_out=*/true, st);
+    B2Z_CUDA(cudaMemcpyAsync(h_out, R.ea.p, n * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, const uint64_t* z, const uint64_t rr[4],
+                                  const uint64_t ss[4], uint8_t proof_out[192]) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk && r && z && rr && ss && proof_out, B2Z_EINVAL, "b2z_groth16_prove_r1cs: NULL argument");
+    R1csImpl& R = r->impl;
+    B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_prove_r1cs: key and matrices disagree");
+    // z goes up once, on the stream that prepares the MSM scalars; the row evaluation reads it on the
+    // main stream after an event
+    cudaEvent_t ev;
+    B2Z_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(ev, c.aux[0]));
+    B2Z_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+    eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, c.stream);
+    prove_on_device_buffers(c, pk, R.ea.p, R.eb.p, R.ec.p, R.z.p, rr, ss, proof_out);
+    cudaEventDestroy(ev);
+  });
+}
+
+}  // extern "C"

@@ -135,8 +135,92 @@ def evaluate_constraint(terms, assignment):
     return acc % R_MOD
 
 
+class ConstraintMatrices:
+    """ark_relations::r1cs::ConstraintMatrices<Fr> in CSR form (what `cs.to_matrices()` returns,
+    flattened): per matrix a (row_ptr uint64[num_constraints + 1], cols uint32[nnz],
+    coeffs uint64[nnz, 4] Montgomery) triple.  upload() puts them on the device once per circuit."""
+
+    def __init__(self, num_instance_variables, num_witness_variables, num_constraints, a, b, c):
+        self.num_instance_variables = num_instance_variables
+        self.num_witness_variables = num_witness_variables
+        self.num_constraints = num_constraints
+        self.a, self.b, self.c = (self._check(m, num_constraints) for m in (a, b, c))
+        self._ctx = None
+        self._handle = None
+
+    @staticmethod
+    def _check(mat, nc):
+        rp = np.ascontiguousarray(mat[0], dtype=np.uint64)
+        cols = np.ascontiguousarray(mat[1], dtype=np.uint32)
+        cf = np.ascontiguousarray(mat[2], dtype=np.uint64).reshape(-1, 4)
+        if rp.shape[0] != nc + 1 or cols.shape[0] != int(rp[-1]) or cf.shape[0] != cols.shape[0]:
+            raise ValueError("inconsistent CSR arrays")
+        return rp, cols, cf
+
+    @property
+    def num_variables(self):
+        return self.num_instance_variables + self.num_witness_variables
+
+    @property
+    def domain_size(self):
+        n = 1
+        while n < self.num_constraints + self.num_instance_variables:
+            n <<= 1
+        return n
+
+    @classmethod
+    def from_rows(cls, num_instance, num_witness, a_rows, b_rows, c_rows):
+        """rows: list (one per constraint) of [(coeff int, column), ...] -- to_matrices() layout."""
+        def csr(rows):
+            lens = np.fromiter((len(r) for r in rows), dtype=np.uint64, count=len(rows))
+            rp = np.zeros(len(rows) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=rp[1:])
+            cols = np.fromiter((col for r in rows for _, col in r), dtype=np.uint32, count=int(rp[-1]))
+            cf = codec.fr_to_mont_limbs([v for r in rows for v, _ in r])
+            return rp, cols, cf
+        return cls(num_instance, num_witness, len(a_rows), csr(a_rows), csr(b_rows), csr(c_rows))
+
+    def rows(self):
+        """Back to (a_rows, b_rows, c_rows) with integer coefficients (host-side consumers: key generation)."""
+        out = []
+        for rp, cols, cf in (self.a, self.b, self.c):
+            vals = codec.fr_from_mont_limbs(cf)
+            out.append([[(vals[k], int(cols[k])) for k in range(int(rp[i]), int(rp[i + 1]))]
+                        for i in range(self.num_constraints)])
+        return tuple(out)
+
+    def upload(self, ctx):
+        if self._handle is not None:
+            return self
+        h = ctypes.c_void_p()
+        args = []
+        for rp, cols, cf in (self.a, self.b, self.c):
+            args += [_ptr(rp), _ptr(cols), _ptr(cf)]
+        ctx.check(ctx._lib.b2z_r1cs_upload(ctx.handle, self.num_constraints, self.num_instance_variables,
+                                           self.num_variables, *args, ctypes.byref(h)))
+        self._ctx, self._handle = ctx, h
+        return self
+
+    def free(self):
+        if self._handle is not None and self._ctx is not None and self._ctx.handle:
+            self._ctx._lib.b2z_r1cs_free(self._ctx.handle, self._handle)
+        self._handle = None
+
+
 class LibsnarkReduction:
     """ark_groth16::r1cs_to_qap::LibsnarkReduction (the R1CSToQAP the reference uses)."""
+
+    @staticmethod
+    def constraint_evaluations_device(ctx, cm, full_assignment):
+        """The same a, b, c vectors computed by the GPU row-evaluation kernel (b2z_r1cs_eval)."""
+        cm.upload(ctx)
+        z = _fr_array(full_assignment)
+        if z.shape[0] != cm.num_variables:
+            raise ValueError("assignment length != number of variables")
+        n = cm.domain_size
+        a, b, c = (np.empty((n, 4), dtype=np.uint64) for _ in range(3))
+        ctx.check(ctx._lib.b2z_r1cs_eval(ctx.handle, cm._handle, _ptr(z), _ptr(a), _ptr(b), _ptr(c)))
+        return a, b, c
 
     @staticmethod
     def constraint_evaluations(matrices, num_inputs, num_constraints, full_assignment):
@@ -169,7 +253,17 @@ class LibsnarkReduction:
 
     @staticmethod
     def witness_map_from_matrices(ctx, matrices, num_inputs, num_constraints, full_assignment):
-        """h coefficients (Montgomery limbs, length = domain size)."""
+        """h coefficients (Montgomery limbs, length = domain size).  `matrices` is either a
+        ConstraintMatrices (everything on the GPU: b2z_witness_map_from_matrices; full_assignment as
+        Montgomery limbs) or the three row lists (rows evaluated on the host in exact integers)."""
+        if isinstance(matrices, ConstraintMatrices):
+            matrices.upload(ctx)
+            z = _fr_array(full_assignment)
+            if z.shape[0] != matrices.num_variables:
+                raise ValueError("assignment length != number of variables")
+            h = np.empty((matrices.domain_size, 4), dtype=np.uint64)
+            ctx.check(ctx._lib.b2z_witness_map_from_matrices(ctx.handle, matrices._handle, _ptr(z), _ptr(h)))
+            return h
         if (num_constraints + num_inputs - 1).bit_length() > 32:
             raise PolynomialDegreeTooLarge("domain exceeds 2^32")
         a, b, c = LibsnarkReduction.constraint_evaluations(matrices, num_inputs, num_constraints, full_assignment)
@@ -322,7 +416,9 @@ class Groth16:
         matrix_proof.rs:129).  The QAP evaluation at tau (LibsnarkReduction::
         instance_map_with_evaluation) is exact integer host work; every group element is
         produced on the GPU by b2z_fixed_base_mul_g1/g2.  Returns (ProvingKey, VerifyingKey)."""
-        a_m, b_m, c_m = matrices
+        cm = matrices if isinstance(matrices, ConstraintMatrices) else None
+        if cm is None:
+            a_m, b_m, c_m = matrices
         l, m = num_instance, num_variables
         n, log_n = 1, 0
         while n < num_constraints + l:
@@ -342,20 +438,43 @@ class Groth16:
         dinv = _batch_inverse([(tau - x) % R_MOD for x in ws])
         zn = zt * pow(n, -1, R_MOD) % R_MOD
         lag = [zn * x % R_MOD * d % R_MOD for x, d in zip(ws, dinv)]
-        at, bt, ct = [0] * m, [0] * m, [0] * m
-        for j in range(l):
-            at[j] = lag[num_constraints + j]
-        for i in range(num_constraints):
-            u = lag[i]
-            for coeff, col in a_m[i]:
-                at[col] += u * coeff
-            for coeff, col in b_m[i]:
-                bt[col] += u * coeff
-            for coeff, col in c_m[i]:
-                ct[col] += u * coeff
-        at = [x % R_MOD for x in at]
-        bt = [x % R_MOD for x in bt]
-        ct = [x % R_MOD for x in ct]
+        if cm is not None:
+            # transposed matrices times the Lagrange vector, on the GPU (b2z_spmv_fr)
+            lag_limbs = codec.fr_to_mont_limbs(lag[:num_constraints])
+
+            def qap(mat):
+                rp, cols, cf = mat
+                nnz = cols.shape[0]
+                rows_of = np.repeat(np.arange(num_constraints, dtype=np.uint32), np.diff(rp.astype(np.int64)))
+                order = np.argsort(cols, kind="stable")
+                t_rp = np.zeros(m + 1, dtype=np.uint64)
+                np.add.at(t_rp, cols.astype(np.int64) + 1, 1)
+                t_rp = np.cumsum(t_rp).astype(np.uint64)
+                t_cols = np.ascontiguousarray(rows_of[order])
+                t_cf = np.ascontiguousarray(cf[order])
+                y = np.zeros((m, 4), dtype=np.uint64)
+                ctx.check(ctx._lib.b2z_spmv_fr(ctx.handle, m, num_constraints, _ptr(t_rp), _ptr(t_cols), _ptr(t_cf),
+                                               _ptr(lag_limbs), _ptr(y)))
+                assert nnz == int(t_rp[-1])
+                return codec.fr_from_mont_limbs(y)
+            at, bt, ct = qap(cm.a), qap(cm.b), qap(cm.c)
+            for j in range(l):
+                at[j] = (at[j] + lag[num_constraints + j]) % R_MOD
+        else:
+            at, bt, ct = [0] * m, [0] * m, [0] * m
+            for j in range(l):
+                at[j] = lag[num_constraints + j]
+            for i in range(num_constraints):
+                u = lag[i]
+                for coeff, col in a_m[i]:
+                    at[col] += u * coeff
+                for coeff, col in b_m[i]:
+                    bt[col] += u * coeff
+                for coeff, col in c_m[i]:
+                    ct[col] += u * coeff
+            at = [x % R_MOD for x in at]
+            bt = [x % R_MOD for x in bt]
+            ct = [x % R_MOD for x in ct]
         ginv, dinv_ = pow(gamma, -1, R_MOD), pow(delta, -1, R_MOD)
         abc = [(beta * x + alpha * y + z) % R_MOD for x, y, z in zip(at, bt, ct)]
         hs, t = [], zt * dinv_ % R_MOD
@@ -388,6 +507,19 @@ class Groth16:
         out = np.zeros(192, dtype=np.uint8)
         ctx.check(ctx._lib.b2z_groth16_prove(ctx.handle, pk._handle, _ptr(a), _ptr(b), _ptr(c), _ptr(z),
                                              _ptr(rs[0:1]), _ptr(rs[1:2]), _ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
+    def create_proof_with_matrices(ctx, pk, cm, full_assignment, r, s):
+        """create_proof_with_reduction with the row evaluation on the GPU too: only the assignment
+        (Montgomery limbs) crosses PCIe (b2z_groth16_prove_r1cs)."""
+        pk.upload(ctx)
+        cm.upload(ctx)
+        z = _fr_array(full_assignment)
+        rs = codec.fr_to_mont_limbs([r, s])
+        out = np.zeros(192, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, cm._handle, _ptr(z), _ptr(rs[0:1]),
+                                                  _ptr(rs[1:2]), _ptr(out)))
         return out.tobytes()
 
     @staticmethod
