@@ -100,6 +100,16 @@ template <class C>
 void msm_run(Ctx* ctx, int slot, const MsmBases<C>& bases, const FrEl* d_scalars_main, uint32_t n_main,
              const FrEl* d_scalars_tail, typename C::Xyzz* d_result, cudaStream_t st);
 
+// The same in two halves, so that a proof can run all the light work (sorts) first and then chain
+// the GPU-filling accumulations: msm_sort = digits + counting sort; msm_finish = accumulate (after
+// `wait_before_accum`, signalling `record_after_accum` when the accumulation kernel is done) + reduce.
+template <class C>
+void msm_sort(Ctx* ctx, int slot, const MsmBases<C>& bases, const FrEl* d_scalars_main, uint32_t n_main,
+              const FrEl* d_scalars_tail, cudaStream_t st);
+template <class C>
+void msm_finish(Ctx* ctx, int slot, const MsmBases<C>& bases, typename C::Xyzz* d_result, cudaStream_t st,
+                cudaEvent_t wait_before_accum, cudaEvent_t record_after_accum);
+
 void msm_release_scratch(Ctx* ctx);
 
 // r (device XYZZ[count]) -> affine limbs + infinity flags on the host side layout

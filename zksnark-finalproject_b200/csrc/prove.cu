@@ -130,10 +130,15 @@ struct PkImpl {
   DevBuf<G2::Xyzz> g2_out;     // B
   uint32_t* h_out = nullptr;   // pinned: 3 G1 XYZZ + 1 G2 XYZZ = B2Z_PARTIAL_BYTES
   cudaEvent_t ev_z = nullptr, ev_done[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr}, ev_accum[3] = {nullptr, nullptr, nullptr};
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
     if (ev_z) cudaEventDestroy(ev_z);
     for (auto& e : ev_done)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : ev_sorted)
+      if (e) cudaEventDestroy(e);
+    for (auto& e : ev_accum)
       if (e) cudaEventDestroy(e);
   }
 };
@@ -266,19 +271,32 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   }
   B2Z_CUDA(cudaEventRecord(pk.ev_z, c.aux[0]));
   G1::Xyzz* g1o = pk.g1_out.p;
-  // A (aux0), B (aux1), C_z (aux2)
-  msm_run<G1>(&c, 1, pk.g1_all, pk.scal_a.p, pk.n1, nullptr, g1o + 0, c.aux[0]);
-  B2Z_CUDA(cudaEventRecord(pk.ev_done[0], c.aux[0]));
+  // ---- light phase: every sort and the witness map, concurrently on four streams
+  msm_sort<G1>(&c, 1, pk.g1_all, pk.scal_a.p, pk.n1, nullptr, c.aux[0]);                      // A
+  B2Z_CUDA(cudaEventRecord(pk.ev_sorted[0], c.aux[0]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], pk.ev_z, 0));
-  msm_run<G2>(&c, 2, pk.g2, pk.scal_a.p, pk.ma, pk.tail.p, pk.g2_out.p, c.aux[1]);
-  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], c.aux[1]));
+  msm_sort<G2>(&c, 2, pk.g2, pk.scal_a.p, pk.ma, pk.tail.p, c.aux[1]);                        // B
+  B2Z_CUDA(cudaEventRecord(pk.ev_sorted[1], c.aux[1]));
   B2Z_CUDA(cudaStreamWaitEvent(c.aux[2], pk.ev_z, 0));
-  msm_run<G1>(&c, 3, pk.g1_all, pk.scal_c.p, pk.n1, nullptr, g1o + 1, c.aux[2]);
-  B2Z_CUDA(cudaEventRecord(pk.ev_done[2], c.aux[2]));
-  // witness map (whole domain, every shard) + this shard's slice of C_h on the main stream
-  witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);
+  msm_sort<G1>(&c, 3, pk.g1_all, pk.scal_c.p, pk.n1, nullptr, c.aux[2]);                      // C_z
+  B2Z_CUDA(cudaEventRecord(pk.ev_sorted[2], c.aux[2]));
+  witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);                 // whole domain, every shard
   fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
-  msm_run<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, g1o + 2, st);
+  msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);                                     // C_h
+  B2Z_CUDA(cudaEventRecord(pk.ev_sorted[3], st));
+  // ---- heavy phase: each accumulation fills the GPU, so they run back to back (B first: its tail is
+  // the longest and overlaps the G1 accumulations); every tail stays on its own stream
+  // (B waits for the z-only sorts so that they are not starved behind it; the witness map and the
+  // C_h sort keep running on the high-priority stream in the gaps the G1 accumulations leave)
+  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], pk.ev_sorted[0], 0));
+  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], pk.ev_sorted[2], 0));
+  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, c.aux[1], nullptr, pk.ev_accum[0]);
+  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], c.aux[1]));
+  msm_finish<G1>(&c, 1, pk.g1_all, g1o + 0, c.aux[0], pk.ev_accum[0], pk.ev_accum[1]);
+  B2Z_CUDA(cudaEventRecord(pk.ev_done[0], c.aux[0]));
+  msm_finish<G1>(&c, 3, pk.g1_all, g1o + 1, c.aux[2], pk.ev_accum[1], pk.ev_accum[2]);
+  B2Z_CUDA(cudaEventRecord(pk.ev_done[2], c.aux[2]));
+  msm_finish<G1>(&c, 0, pk.h, g1o + 2, st, pk.ev_accum[2], nullptr);
   for (auto& e : pk.ev_done) B2Z_CUDA(cudaStreamWaitEvent(st, e, 0));
   B2Z_CUDA(cudaMemcpyAsync(pk.h_out, g1o, 3 * kG1Bytes, cudaMemcpyDeviceToHost, st));
   B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 3 * kG1Bytes / 4, pk.g2_out.p, kG2Bytes, cudaMemcpyDeviceToHost, st));
@@ -464,6 +482,8 @@ b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank
     B2Z_CUDA(cudaMallocHost(&P.h_out, kPartialBytes));
     B2Z_CUDA(cudaEventCreateWithFlags(&P.ev_z, cudaEventDisableTiming));
     for (auto& e : P.ev_done) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : P.ev_sorted) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : P.ev_accum) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = pk.release();
   });
 }
