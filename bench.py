@@ -434,7 +434,7 @@ def main():
                                    (key_bytes / 1e6, (3 * n + m) * 32 / 1e6)},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "proofs/s", "ms_per_step": e2e_dev_s / args.steps * 1e3,
-                "h2d_bytes_per_step": int(m * 32 + 64), "d2h_bytes_per_step": 960,
+                "h2d_bytes_per_step": int(m * 32 + 64), "d2h_bytes_per_step": 1344,
                 "call": "b2z_groth16_prove_r1cs (row evaluation + witness map + 4 MSMs + host epilogue)"},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_s / args.steps * 1e3,

@@ -151,9 +151,10 @@ B2Z_API b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
  * a / b_g1 / b_g2 / l queries and the same fraction of the (bit-reversed) h bases; rank 0 also
  * keeps the alpha/beta/delta terms.  Every rank passes the SAME full desc and the same full
  * a/b/c/z/r/s; the witness map runs on every rank.  Each rank gets B2Z_PARTIAL_BYTES of partial
- * sums (XYZZ limbs: A | C_z | C_h in G1, B in G2); gather them over any transport (NCCL
- * all_gather of 960 bytes per rank) and finish on the host with b2z_groth16_combine.          */
-#define B2Z_PARTIAL_BYTES 960
+ * sums (XYZZ limbs: A | s*A | r*B1 | L | H in G1, B in G2 -- scalar multiplication is linear, so
+ * every rank applies s and r to its own partial A and B1); gather them over any transport (NCCL
+ * all_gather of 1344 bytes per rank) and finish on the host with b2z_groth16_combine.         */
+#define B2Z_PARTIAL_BYTES 1344
 B2Z_API b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* desc, uint32_t rank, uint32_t world,
                                        b2z_pk** out);
 B2Z_API b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk, const uint64_t* a_evals,

@@ -38,20 +38,21 @@ def oracle_partial(codec, opk, inst, h, r, s, rank, world):
     j1, j2 = O.G1, O.G2
     A = OG.msm_naive(j1, opk.a_query[lo:hi], z[lo:hi])
     B = OG.msm_naive(j2, opk.b_g2_query[lo:hi], z[lo:hi])
-    Cz = OG.msm_naive(j1, opk.a_query[lo:hi], [s * x % R for x in z[lo:hi]])
-    Cz = j1.jadd(Cz, OG.msm_naive(j1, opk.b_g1_query[lo:hi], [r * x % R for x in z[lo:hi]]))
-    Cz = j1.jadd(Cz, OG.msm_naive(j1, opk.l_query[l_lo - l:l_hi - l], z[l_lo:l_hi]))
+    B1 = OG.msm_naive(j1, opk.b_g1_query[lo:hi], z[lo:hi])
+    Lp = OG.msm_naive(j1, opk.l_query[l_lo - l:l_hi - l], z[l_lo:l_hi])
     if rank == 0:
         A = j1.jadd(A, OG.msm_naive(j1, [opk.alpha_g1, opk.delta_g1], [1, r]))
         B = j2.jadd(B, OG.msm_naive(j2, [opk.beta_g2, opk.delta_g2], [1, s]))
-        Cz = j1.jadd(Cz, OG.msm_naive(j1, [opk.alpha_g1, opk.beta_g1, opk.delta_g1], [s, r, r * s % R]))
+        B1 = j1.jadd(B1, OG.msm_naive(j1, [opk.beta_g1, opk.delta_g1], [1, s]))
+        Lp = j1.jadd(Lp, j1.jmul(j1.to_jac(opk.delta_g1), (-(r * s)) % R))
+    sA, rB1 = j1.jmul(A, s), j1.jmul(B1, r)
     # h positions are in bit-reversed order on the device
     lg = n.bit_length() - 1
     br = lambda p: int(format(p, "0%db" % lg)[::-1], 2) if lg else 0
     idx = [br(p) for p in range(h_lo, h_hi)]
     Ch = OG.msm_naive(j1, [opk.h_query[i] if i < n - 1 else None for i in idx], [h[i] for i in idx])
-    return b"".join([xyzz_limbs(codec, O.G1, j1.to_affine(A)), xyzz_limbs(codec, O.G1, j1.to_affine(Cz)),
-                     xyzz_limbs(codec, O.G1, j1.to_affine(Ch)), xyzz_limbs(codec, O.G2, j2.to_affine(B))])
+    return b"".join([xyzz_limbs(codec, O.G1, j1.to_affine(P)) for P in (A, sA, rB1, Lp, Ch)] +
+                    [xyzz_limbs(codec, O.G2, j2.to_affine(B))])
 
 
 def test_combine_matches_golden_single_process(b2z, circuits, golden):

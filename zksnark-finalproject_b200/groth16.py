@@ -550,7 +550,7 @@ class Groth16:
     @staticmethod
     def create_proof_sharded(ctx, pk, a, b, c, full_assignment, r, s, group=None):
         """One proof computed by all ranks of a torch.distributed group (one process per GPU):
-        partial sums on every rank, one all_gather of 960 bytes per rank, host combine.
+        partial sums on every rank, one all_gather of B2Z_PARTIAL_BYTES per rank, host combine.
         Returns the proof bytes on every rank."""
         import torch
         import torch.distributed as dist
