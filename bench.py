@@ -333,15 +333,15 @@ def main():
         out = {}
 
         def step_sharded():
-            ctx.check(L.b2z_groth16_prove_partial(ctx.handle, spk._handle, hp(host[0]), hp(host[1]), hp(host[2]),
-                                                  hp(host[3]), p(rs0[0:1]), p(rs0[1:2]), p(part)))
+            ctx.check(L.b2z_groth16_prove_partial_r1cs(ctx.handle, spk._handle, inst.cm._handle, hp(host[3]),
+                                                       p(rs0[0:1]), p(rs0[1:2]), p(part)))
             dist.all_gather(gathered, torch.from_numpy(part).cuda())
             out["proof"] = pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered])
 
         step_sharded()
         ref = np.zeros(192, dtype=np.uint8)
-        ctx.check(L.b2z_groth16_prove(ctx.handle, pk._handle, hp(host[0]), hp(host[1]), hp(host[2]), hp(host[3]),
-                                      p(rs0[0:1]), p(rs0[1:2]), p(ref)))
+        ctx.check(L.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, inst.cm._handle, hp(host[3]), p(rs0[0:1]),
+                                           p(rs0[1:2]), p(ref)))
         assert out["proof"] == ref.tobytes(), "sharded proof differs from the single-GPU proof"
         for _ in range(args.warmup):
             step_sharded()

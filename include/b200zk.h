@@ -160,6 +160,9 @@ B2Z_API b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* desc, ui
 B2Z_API b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk, const uint64_t* a_evals,
                                              const uint64_t* b_evals, const uint64_t* c_evals, const uint64_t* z,
                                              const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);
+/* the same with the constraint rows evaluated on the GPU: only z crosses PCIe on every rank */
+B2Z_API b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r1cs, const uint64_t* z,
+                                                  const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);
 /* host only (no GPU, no ctx): partials = world x B2Z_PARTIAL_BYTES in rank order */
 B2Z_API b2z_status b2z_groth16_combine(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]);
 

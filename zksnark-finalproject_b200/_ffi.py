@@ -48,6 +48,7 @@ SIGNATURES = {
     "b2z_pk_upload_shard": (ctypes.c_int32, [vp, ctypes.POINTER(PkDesc), ctypes.c_uint32, ctypes.c_uint32,
                                              ctypes.POINTER(vp)]),
     "b2z_groth16_prove_partial": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2z_groth16_prove_partial_r1cs": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp]),
     "b2z_groth16_combine": (ctypes.c_int32, [vp, ctypes.c_uint32, vp]),
     "b2z_groth16_prove_device": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2z_fixed_base_mul_g1": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, vp, vp]),

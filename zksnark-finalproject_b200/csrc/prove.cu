@@ -333,6 +333,10 @@ void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrE
                              const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]) {
   prove_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, proof_out);
 }
+void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
+                                     const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out) {
+  prove_partial_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, partial_out);
+}
 }  // namespace b2z
 
 extern "C" {

@@ -9,4 +9,7 @@ bool pk_matches(const b2z_pk* pk, uint32_t log_n, uint64_t m, uint64_t l);
 // whole-key proof from device-resident a/b/c evaluations (clobbered) and assignment
 void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
                              const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+// the same for one shard of a key: B2Z_PARTIAL_BYTES of partial sums
+void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
+                                     const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);
 }  // namespace b2z

@@ -219,4 +219,21 @@ b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, c
   });
 }
 
+b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, const uint64_t* z,
+                                          const uint64_t rr[4], const uint64_t ss[4], uint8_t* partial_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk && r && z && rr && ss && partial_out, B2Z_EINVAL, "b2z_groth16_prove_partial_r1cs: NULL argument");
+    R1csImpl& R = r->impl;
+    B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_prove_partial_r1cs: key and matrices disagree");
+    cudaEvent_t ev;
+    B2Z_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(ev, c.aux[0]));
+    B2Z_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+    eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, c.stream);
+    prove_partial_on_device_buffers(c, pk, R.ea.p, R.eb.p, R.ec.p, R.z.p, rr, ss, partial_out);
+    cudaEventDestroy(ev);
+  });
+}
+
 }  // extern "C"

@@ -536,6 +536,17 @@ class Groth16:
         return out.tobytes()
 
     @staticmethod
+    def create_proof_partial_with_matrices(ctx, pk, cm, full_assignment, r, s):
+        """create_proof_partial with the constraint rows evaluated on the GPU (only z crosses PCIe)."""
+        cm.upload(ctx)
+        z = _fr_array(full_assignment)
+        rs = codec.fr_to_mont_limbs([r, s])
+        out = np.zeros(_ffi.PARTIAL_BYTES, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_groth16_prove_partial_r1cs(ctx.handle, pk._handle, cm._handle, _ptr(z), _ptr(rs[0:1]),
+                                                          _ptr(rs[1:2]), _ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
     def combine(partials):
         """b2z_groth16_combine: host-only sum of the shards' partials (rank order) -> 192 proof bytes."""
         buf = np.frombuffer(b"".join(partials), dtype=np.uint8).copy()
@@ -548,13 +559,16 @@ class Groth16:
         return out.tobytes()
 
     @staticmethod
-    def create_proof_sharded(ctx, pk, a, b, c, full_assignment, r, s, group=None):
+    def create_proof_sharded(ctx, pk, a, b, c, full_assignment, r, s, group=None, cm=None):
         """One proof computed by all ranks of a torch.distributed group (one process per GPU):
         partial sums on every rank, one all_gather of B2Z_PARTIAL_BYTES per rank, host combine.
         Returns the proof bytes on every rank."""
         import torch
         import torch.distributed as dist
-        mine = Groth16.create_proof_partial(ctx, pk, a, b, c, full_assignment, r, s)
+        if cm is not None:
+            mine = Groth16.create_proof_partial_with_matrices(ctx, pk, cm, full_assignment, r, s)
+        else:
+            mine = Groth16.create_proof_partial(ctx, pk, a, b, c, full_assignment, r, s)
         world = dist.get_world_size(group)
         t = torch.frombuffer(bytearray(mine), dtype=torch.uint8)
         if dist.get_backend(group) == "nccl":
