@@ -44,6 +44,7 @@ WORKLOADS = {
     "c2": "matrix-multiplication 16x16 with Poseidon-shaped hashes (BASELINE configs[1]): "
           "109955 constraints, domain 2^17",
     "m8": "matrix-multiplication 8x8 (development size): domain 2^15",
+    "c3": "prime-SNARK shape (BASELINE configs[2]): 7 SHA-256-sized Boolean blocks + 3 Fermat modpows, NUM_BITS=20",
     "c5": "matrix-multiplication 64x64 with Poseidon-shaped hashes (BASELINE configs[4] shape): "
           "2152451 constraints, domain 2^22",
 }
@@ -62,6 +63,10 @@ def build_instance(name):
     pkg = importlib.import_module(PKG)
     if name == "c1":
         inst = importlib.import_module(PKG + ".circuits").fibonacci_circuit(0, 1, 1000)
+        cm = pkg.ConstraintMatrices.from_rows(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c)
+        return Instance(cm, inst.z)
+    if name == "c3":
+        inst = importlib.import_module(PKG + ".circuits").prime_circuit(5, num_bits=20, k_bases=3, sha_blocks=7)
         cm = pkg.ConstraintMatrices.from_rows(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c)
         return Instance(cm, inst.z)
     n = {"c2": 16, "m8": 8, "c5": 64}[name]

@@ -43,6 +43,12 @@ void b2z_ctx_destroy(b2z_ctx* ctx) {
   cudaDeviceSynchronize();
   ctx->impl.domains.clear();
   msm_release_scratch(&ctx->impl);
+  for (auto& sp : ctx->impl.spans) {
+    cudaEventDestroy(sp.start);
+    cudaEventDestroy(sp.stop);
+    if (sp.units_pinned) cudaFreeHost(sp.units_pinned);
+  }
+  ctx->impl.spans.clear();
   if (ctx->impl.stream) cudaStreamDestroy(ctx->impl.stream);
   for (auto& s : ctx->impl.aux)
     if (s) cudaStreamDestroy(s);

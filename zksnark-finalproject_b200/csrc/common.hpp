@@ -145,6 +145,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<uint32_t, NttDomain> domains;
+  bool ntt_attr_set[3] = {false, false, false};
   bool profile = false;
   std::vector<ProfileSpan> spans;
   std::mutex span_mu;                  // spans are appended from the single calling thread; guards reads

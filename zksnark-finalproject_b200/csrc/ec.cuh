@@ -156,16 +156,6 @@ struct Curve {
   static B2Z_HD_NOINLINE Xyzz madd(const Xyzz& a, const Affine& q) { return madd_inl(a, q); }
   static B2Z_HD_NOINLINE Xyzz add(const Xyzz& a, const Xyzz& b) { return add_inl(a, b); }
 
-  // k * p for a small unsigned k (bucket-chunk offsets), double-and-add.
-  static B2Z_HD_NOINLINE Xyzz mul_small(const Xyzz& p, uint32_t k) {
-    Xyzz acc = identity();
-    for (int i = 31; i >= 0; i--) {
-      acc = dbl(acc);
-      if ((k >> i) & 1) acc = add(acc, p);
-    }
-    return acc;
-  }
-
   // k * p for a 256-bit little-endian scalar (8 x u32).
   static B2Z_HD_NOINLINE Xyzz mul_scalar(const Xyzz& p, const uint32_t* k) {
     Xyzz acc = identity();

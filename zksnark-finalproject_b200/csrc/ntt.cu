@@ -197,11 +197,11 @@ void launch_pass(Ctx* ctx, FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint3
   const uint32_t S = 1u << ls;
   const uint32_t threads = S / 8 < 32 ? 32 : S / 8;
   const size_t smem = (size_t)2 * (S + (S >> 3)) * sizeof(uint4);
-  static bool attr_set[3] = {false, false, false};
-  if (!attr_set[MODE]) {
+  // per-device function attribute (a process may hold contexts on several GPUs): set it once per context
+  if (!ctx->ntt_attr_set[MODE]) {
     B2Z_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   2 * ((1 << kMaxTileLog) + (1 << (kMaxTileLog - 3))) * (int)sizeof(uint4)));
-    attr_set[MODE] = true;
+    ctx->ntt_attr_set[MODE] = true;
   }
   const uint32_t grid = 1u << (log_n - ls);
   ProfileScope ps(ctx, PH_NTT_PASS, st, (uint64_t)1 << log_n);

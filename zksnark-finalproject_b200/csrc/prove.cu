@@ -111,7 +111,7 @@ struct PkImpl {
   DevBuf<G2::Xyzz> g2_out;     // B
   uint32_t* h_out = nullptr;   // pinned: B2Z_PARTIAL_BYTES
   cudaEvent_t ev_z = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_sorted[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_accum[4] = {nullptr, nullptr, nullptr, nullptr};
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
@@ -267,7 +267,9 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   // exactly that), so the light work, the tails of A and B1 and the two scalar multiplications overlap
   // the following G1 accumulations.  The G2 accumulation (255 registers: it fills every SM, nothing can
   // be scheduled beside it) goes last so that nothing waits behind it except its own tail.  Measured on
-  // the C2 workload: this order 7.65 ms per proof, G2-first 8.3 ms (s*A lands on the critical path).
+  // the C2 workload: this order 7.65 ms per proof; G2 first 8.3 ms, G2 before H 7.8 ms, G2 first with 8 SMs
+  // left out of its grid 8.3 ms -- in each of those a tail stretched by a concurrent accumulation pushes
+  // s*A or r*B1 onto the critical path.
   msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, nullptr, pk.ev_accum[0]);
   scalar_mul_coop_kernel<<<1, 32, 0, sA>>>(g1o + 0, s_c, g1o + 1);                // s * A
   B2Z_LAUNCHED(&c);
