@@ -1,8 +1,11 @@
 // Host-side Fq / Fq2 arithmetic (64-bit limbs, unsigned __int128) for the O(1)
-// epilogue of a proof: one point addition, three affine normalisations (one field
-// inversion each) and the zcash-format serialization -- what ark-groth16 does with
-// `into_affine()` and ark-serialize's `serialize_compressed` after its MSMs
-// (SURVEY.md section 7, step 9 keeps this on the host).  A 381-bit inversion is
+// epilogue of a proof: the two scalar multiplications s*A and r*B1 (arkworks'
+// `mul_bigint` on freshly computed points: ~380 dependent point operations each, 0.2 ms
+// on a CPU core, 1.5 ms even with lane-cooperative arithmetic on the GPU -- they run here
+// WHILE the GPU is still busy with the remaining MSMs), a few point additions, three
+// affine normalisations (one field inversion each) and the zcash-format serialization --
+// what ark-groth16 does with `into_affine()` and ark-serialize's `serialize_compressed`
+// after its MSMs (SURVEY.md section 7, step 9 keeps this on the host).  A 381-bit inversion is
 // ~25 us here versus ~0.6 ms for a lone GPU thread, and the three results have to
 // cross PCIe anyway.  Nothing proportional to the circuit size runs on the host.
 #pragma once
@@ -231,6 +234,21 @@ inline G2Xyzz g2_add(const G2Xyzz& a, const G2Xyzz& b) {
   o.zzz = fq2_mul(fq2_mul(a.zzz, b.zzz), ppp);
   return o;
 }
+
+// k * p for a canonical 256-bit little-endian scalar (8 x u32): arkworks' `mul_bigint`
+// (double-and-add, MSB first).  ~0.2 ms on one core.
+inline G1Xyzz g1_mul_scalar(const G1Xyzz& p, const uint32_t k[8]) {
+  G1Xyzz acc;
+  std::memset(&acc, 0, sizeof(acc));
+  int top = 255;
+  while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1)) top--;
+  for (int i = top; i >= 0; i--) {
+    acc = g1_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) acc = g1_add(acc, p);
+  }
+  return acc;
+}
+inline void g1_to_device_layout(const G1Xyzz& p, uint32_t* w) { std::memcpy(w, &p, sizeof(p)); }
 
 // affine normalisation (Montgomery coordinates); returns true for the identity
 inline bool g1_to_affine(const G1Xyzz& p, Fq* x, Fq* y) {

@@ -15,16 +15,15 @@
 //   B   : G2 [b_g2     | beta_2  delta_2]   x [z | 1 s]
 // All of them read z as it is (small / Boolean witness values keep their few non-zero digits).
 // s*A and r*B1 -- 255-bit double-and-add on freshly computed points, the one inherently serial
-// piece of arkworks' formulation -- run as ONE lane group each with the cooperative point
-// arithmetic of ec_coop.cuh (~1.5 ms) on the streams of A and B1, overlapped by the L / H
-// accumulations.  Schedule: light work first (scalar prep, all sorts, witness map), then the
+// piece of arkworks' formulation -- are done where arkworks does them, on the host, as soon as A
+// and B1 have been copied back and WHILE the GPU is still accumulating L and H (0.2 ms each on a
+// CPU core).  Schedule: light work first (scalar prep, all sorts, witness map), then the
 // GPU-filling accumulations chained back to back, each tail overlapping the next accumulation.
-// The host finishes with three point additions, three affine normalisations and the
+// The host finishes with a few point additions, three affine normalisations and the
 // serialization (host_fq.hpp).  r = 0: r*B1 is the identity, exactly arkworks' special case.
 #include <cstring>
 
 #include "api_glue.hpp"
-#include "ec_coop.cuh"
 #include "host_fq.hpp"
 #include "msm.hpp"
 #include "prove_internal.hpp"
@@ -63,24 +62,6 @@ __global__ void pack_flags_kernel2(const uint32_t* flags, uint32_t n, uint32_t* 
   words[w] = v;
 }
 
-// out = k * in for a canonical 255-bit scalar: one lane group, cooperative double-and-add
-__global__ void scalar_mul_coop_kernel(const G1::Xyzz* in, FrEl k, G1::Xyzz* out) {
-  using K = Coop<Fq>;
-  __shared__ K::Scratch sc;
-  __shared__ G1::Xyzz acc, base;
-  const K::LG g;
-  if (blockIdx.x != 0 || threadIdx.x >= K::GROUP) return;
-  K::copy(g, &base, in);
-  K::set_identity(g, &acc);
-  int top = 255;
-  while (top >= 0 && !((k.l[top >> 5] >> (top & 31)) & 1)) top--;
-  for (int i = top; i >= 0; i--) {
-    K::dbl(g, &sc, &acc, &acc);
-    if ((k.l[i >> 5] >> (i & 31)) & 1) K::add(g, &sc, &acc, &base, &acc);
-  }
-  K::copy(g, out, &acc);
-}
-
 inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
 
 FrEl fr_load_host(const uint64_t v[4]) {
@@ -107,14 +88,16 @@ struct PkImpl {
   MsmBases<G2> g2;             // [b_g2     | beta_2  delta_2]
   // per-proof device scratch
   DevBuf<FrEl> ea, eb, ec, z, zc, hc, tail;
-  DevBuf<G1::Xyzz> g1_out;     // A, sA, rB1, L, H, B1
+  DevBuf<G1::Xyzz> g1_out;     // 0 A, 3 L, 4 H, 5 B1 (1, 2 unused: s*A and r*B1 are made on the host)
   DevBuf<G2::Xyzz> g2_out;     // B
   uint32_t* h_out = nullptr;   // pinned: B2Z_PARTIAL_BYTES
+  uint32_t* h_b1 = nullptr;    // pinned: B1 (input of the host-side r*B1)
   cudaEvent_t ev_z = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_accum[4] = {nullptr, nullptr, nullptr, nullptr};
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
+    if (h_b1) cudaFreeHost(h_b1);
     if (ev_z) cudaEventDestroy(ev_z);
     for (auto& e : ev_done)
       if (e) cudaEventDestroy(e);
@@ -262,30 +245,38 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);    // whole domain, every shard
   fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
   msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);
-  // ---- heavy phase: A -> B1 -> L -> H -> B, accumulations chained by events.  A G1 accumulation
-  // leaves room on every SM for sort / NTT / tail blocks (the tail kernels are register-capped for
-  // exactly that), so the light work, the tails of A and B1 and the two scalar multiplications overlap
-  // the following G1 accumulations.  The G2 accumulation (255 registers: it fills every SM, nothing can
-  // be scheduled beside it) goes last so that nothing waits behind it except its own tail.  Measured on
-  // the C2 workload: this order 7.65 ms per proof; G2 first 8.3 ms, G2 before H 7.8 ms, G2 first with 8 SMs
-  // left out of its grid 8.3 ms -- in each of those a tail stretched by a concurrent accumulation pushes
-  // s*A or r*B1 onto the critical path.
-  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, nullptr, pk.ev_accum[0]);
-  scalar_mul_coop_kernel<<<1, 32, 0, sA>>>(g1o + 0, s_c, g1o + 1);                // s * A
-  B2Z_LAUNCHED(&c);
+  // ---- heavy phase: B -> A -> B1 -> L -> H, accumulations chained by events.
+  // The G2 accumulation (255 registers: it fills every SM, nothing can be scheduled beside it) goes
+  // first, right after the z-only sorts, so that its tail -- the longest -- hides under the G1
+  // accumulations.  A G1 accumulation leaves room on every SM for sort / NTT / tail blocks (the tail
+  // kernels are register-capped for exactly that), so the witness map and the other tails overlap too.
+  // s*A and r*B1 are computed by the HOST as soon as A and B1 arrive (0.2 ms each), while the GPU is
+  // still busy with L and H.  (With the scalar multiplications on the GPU -- 1.5 ms each even with
+  // lane-cooperative arithmetic -- every order tried put one of them on the critical path: 7.65-8.3 ms
+  // per C2 proof.)
+  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
+  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
+  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
+  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3]);
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 5 * kG1Bytes / 4, pk.g2_out.p, kG2Bytes, cudaMemcpyDeviceToHost, sB));
+  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
+  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, pk.ev_accum[3], pk.ev_accum[0]);
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 0 * kG1Bytes / 4, g1o + 0, kG1Bytes, cudaMemcpyDeviceToHost, sA));
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], sA));
   msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, pk.ev_accum[0], pk.ev_accum[1]);
-  scalar_mul_coop_kernel<<<1, 32, 0, sB1>>>(g1o + 5, r_c, g1o + 2);               // r * B1
-  B2Z_LAUNCHED(&c);
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_b1, g1o + 5, kG1Bytes, cudaMemcpyDeviceToHost, sB1));
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], sB1));
   msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, pk.ev_accum[1], pk.ev_accum[2]);
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 3 * kG1Bytes / 4, g1o + 3, kG1Bytes, cudaMemcpyDeviceToHost, sL));
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], sL));
-  msm_finish<G1>(&c, 0, pk.h, g1o + 4, st, pk.ev_accum[2], pk.ev_accum[3]);
-  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, pk.ev_accum[3], nullptr);
-  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
-  for (auto& e : pk.ev_done) B2Z_CUDA(cudaStreamWaitEvent(st, e, 0));
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out, g1o, 5 * kG1Bytes, cudaMemcpyDeviceToHost, st));
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 5 * kG1Bytes / 4, pk.g2_out.p, kG2Bytes, cudaMemcpyDeviceToHost, st));
+  msm_finish<G1>(&c, 0, pk.h, g1o + 4, st, pk.ev_accum[2], nullptr);
+  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 4 * kG1Bytes / 4, g1o + 4, kG1Bytes, cudaMemcpyDeviceToHost, st));
+  // host: s*A and r*B1 while the GPU works on L and H
+  B2Z_CUDA(cudaEventSynchronize(pk.ev_done[0]));
+  host::g1_to_device_layout(host::g1_mul_scalar(host::g1_from_device(pk.h_out), s_c.l), pk.h_out + 1 * kG1Bytes / 4);
+  B2Z_CUDA(cudaEventSynchronize(pk.ev_done[2]));
+  host::g1_to_device_layout(host::g1_mul_scalar(host::g1_from_device(pk.h_b1), r_c.l), pk.h_out + 2 * kG1Bytes / 4);
+  for (auto& e : pk.ev_done) B2Z_CUDA(cudaEventSynchronize(e));
   B2Z_CUDA(cudaStreamSynchronize(st));
   std::memcpy(partial_out, pk.h_out, kPartialBytes);
 }
@@ -469,6 +460,7 @@ b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank
     P.z.alloc(m); P.zc.alloc(P.ma ? P.ma : 1); P.tail.alloc(5);
     P.g1_out.alloc(6); P.g2_out.alloc(1);
     B2Z_CUDA(cudaMallocHost(&P.h_out, kPartialBytes));
+    B2Z_CUDA(cudaMallocHost(&P.h_b1, kG1Bytes));
     B2Z_CUDA(cudaEventCreateWithFlags(&P.ev_z, cudaEventDisableTiming));
     for (auto& e : P.ev_done) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : P.ev_sorted) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
