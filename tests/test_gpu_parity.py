@@ -398,6 +398,32 @@ def test_prove_point_sharded_equals_whole_key(b2z, ctx, codec, circuits, world):
     pk.free()
 
 
+def test_prove_degenerate_shapes(b2z, ctx, codec, cpu_oracle, circuits):
+    """Edge shapes: a system with a single witness and nearly empty rows (Fibonacci, 0 steps: one
+    constraint, domain 8), more shards than variables, and an all-zero witness vector."""
+    inst = circuits.fibonacci_circuit(3, 4, 0)
+    assert inst.num_constraints == 1 and inst.num_witness == 1
+    _setup_prove_verify(b2z, ctx, codec, cpu_oracle, inst, 21)
+    # shards outnumber the 5 variables: some ranks hold no query points at all
+    rnd = random.Random(5)
+    toxic = [rnd.randrange(1, R) for _ in range(5)]
+    inst = circuits.fibonacci_circuit(0, 0, 3)          # all-zero assignment except the constant 1
+    assert inst.is_satisfied() and sum(inst.z) == 1
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+                                                      inst.num_variables, *toxic)
+    want, (a, b, c) = _prove_gpu(b2z, ctx, codec, pk, inst, 11, 22)
+    z = codec.fr_to_mont_limbs(inst.z)
+    parts = []
+    for k in range(7):
+        shard = b2z.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                               pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                               pk.beta_g2, pk.delta_g2).upload(ctx, rank=k, world=7)
+        parts.append(b2z.Groth16.create_proof_partial(ctx, shard, a, b, c, z, 11, 22))
+        shard.free()
+    assert b2z.Groth16.combine(parts) == want
+    pk.free()
+
+
 # ------------------------------------------------------------------------------- error behaviour
 def test_error_codes(b2z, ctx):
     import ctypes

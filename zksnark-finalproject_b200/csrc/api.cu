@@ -20,15 +20,15 @@ b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
   ctx->impl.device = device_id;
   try {
     B2Z_CUDA(cudaSetDevice(device_id));
-    // the main stream carries the witness map and the MSM that depends on it (the critical
-    // path of a proof): its blocks are scheduled ahead of the z-only MSMs on the aux streams
+    // The aux streams carry the z-only MSMs, whose sorts gate the first (GPU-filling) accumulation:
+    // they get the higher priority so that those sorts are not slowed by the witness map, which runs
+    // on the main stream and is only needed by the LAST accumulation (H) -- it has the whole heavy
+    // phase to finish in the room the G1 accumulations leave.
     int prio_lo = 0, prio_hi = 0;
     B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_hi));
-    // aux[1] carries the G2 MSM, whose tail is the longest: let it finish its accumulation early
-    // so that its bucket reduction overlaps the G1 accumulations instead of trailing them
+    B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_lo));
     for (int i = 0; i < 4; i++)
-      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, i == 1 ? prio_hi : prio_lo));
+      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, prio_hi));
   } catch (const StatusError& e) {
     delete ctx;
     return e.code;
