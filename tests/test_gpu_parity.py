@@ -424,6 +424,50 @@ def test_prove_degenerate_shapes(b2z, ctx, codec, cpu_oracle, circuits):
     pk.free()
 
 
+def test_prove_from_concurrent_host_threads(b2z, ctx, codec, circuits):
+    """The reference serves proofs from several actix worker threads (src/main.rs:37).  Three host
+    threads prove at the same time -- two with their own context and key copy, one sharing the session
+    context with the main thread (calls on one context serialise) -- and every proof equals the
+    single-threaded bytes."""
+    import threading
+    inst = circuits.matrix_circuit([[1, 2, 3], [4, 5, 6], [7, 8, 9]], [[9, 8, 7], [6, 5, 4], [3, 2, 1]])
+    opk = OG.setup(oracle_r1cs(inst), seed=77)
+    limbs = pk_limbs(codec, opk)
+    a, b, c = b2z.LibsnarkReduction.constraint_evaluations(inst.matrices, inst.num_instance, inst.num_constraints, inst.z)
+    z = codec.fr_to_mont_limbs(inst.z)
+    pairs = [(3 + 5 * i, 11 + 7 * i) for i in range(4)]
+    shared_pk = b2z.ProvingKey(*limbs).upload(ctx)
+    want = [b2z.Groth16.create_proof_with_reduction(ctx, shared_pk, a, b, c, z, r, s) for r, s in pairs]
+    assert len(set(want)) == len(pairs)
+    results, errors = {}, []
+
+    def worker(name, own):
+        try:
+            wctx = b2z.Context(0) if own else ctx
+            wpk = b2z.ProvingKey(*limbs).upload(wctx) if own else shared_pk
+            out = []
+            for _ in range(3):
+                out.append([b2z.Groth16.create_proof_with_reduction(wctx, wpk, a, b, c, z, r, s) for r, s in pairs])
+            results[name] = out
+            if own:
+                wpk.free()
+                wctx.close()
+        except Exception as e:          # surfaced below: a thread must not die silently
+            errors.append((name, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(n, own)) for n, own in (("w0", True), ("w1", True), ("shared", False))]
+    for t in threads:
+        t.start()
+    main_out = [b2z.Groth16.create_proof_with_reduction(ctx, shared_pk, a, b, c, z, r, s) for r, s in pairs]
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert main_out == want
+    for name in ("w0", "w1", "shared"):
+        assert all(rep == want for rep in results[name]), name
+    shared_pk.free()
+
+
 # ------------------------------------------------------------------------------- error behaviour
 def test_error_codes(b2z, ctx):
     import ctypes
