@@ -12,14 +12,15 @@ KREGEX='regex:msm_|ntt_|wm_|scalar_prep|fr_from_mont|canonicalize|scan_|bitrev|p
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s $SKIP -c 100 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
-# accumulation launches per proof: A (G1), B (G2), C_z (G1), C_h (G1)  ->  index 14 = C_z, 13 = B
-ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 14 -c 1 \
+# accumulation launches per proof, in issue order: B (G2), A, B1, L, H (G1); 3 warm-up proofs = 15 launches
+# -> index 15 = B (G2), 16 = A (G1) of the first timed proof
+ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 16 -c 1 \
     -o gpurun_out/prof_accum_g1 $CMD > gpurun_out/ncu_full_accum_g1.log 2>&1
 echo "full accum g1 exit $?"
-ncu --set full --clock-control none -k regex:msm_accum_kernel -s 13 -c 1 \
+ncu --set full --clock-control none -k regex:msm_accum_kernel -s 15 -c 1 \
     -o gpurun_out/prof_accum_g2 $CMD > gpurun_out/ncu_full_accum_g2.log 2>&1
 echo "full accum g2 exit $?"
-ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 45 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 36 -c 2 \
     -o gpurun_out/prof_ntt $CMD > gpurun_out/ncu_full_ntt.log 2>&1
 echo "full ntt exit $?"
 for f in prof_accum_g1 prof_accum_g2 prof_ntt; do

@@ -292,6 +292,24 @@ inline void g2_serialize(uint8_t* dst, const G2Xyzz& p) {
   if (larger) dst[0] |= 0x20;
 }
 
+// Last step of the MSM bucket reduction, done here because it is strictly serial (msm.hpp,
+// MsmHostPlanes): planes[0] + 2^chunk_log * sum_{k >= 1} 2^(k-1) planes[k].
+inline G1Xyzz g1_identity() { G1Xyzz r; r.x = r.y = r.zz = r.zzz = fq_zero(); return r; }
+inline G2Xyzz g2_identity() { G2Xyzz r; r.x = r.y = r.zz = r.zzz = Fq2{fq_zero(), fq_zero()}; return r; }
+template <class P, class FromDev, class Dbl, class Add>
+inline P planes_horner_generic(const uint32_t* dev_planes, uint32_t words_per_point, uint32_t nplanes, uint32_t chunk_log,
+                               P identity, FromDev from_dev, Dbl dbl, Add add) {
+  if (nplanes == 0) return identity;
+  P acc = from_dev(dev_planes);
+  if (nplanes > 1) {
+    P h = from_dev(dev_planes + (size_t)(nplanes - 1) * words_per_point);
+    for (uint32_t k = nplanes - 1; k-- > 1;) h = add(dbl(h), from_dev(dev_planes + (size_t)k * words_per_point));
+    for (uint32_t i = 0; i < chunk_log; i++) h = dbl(h);
+    acc = add(acc, h);
+  }
+  return acc;
+}
+
 // device XYZZ (32-bit limbs, lazily reduced) -> host structs
 inline G1Xyzz g1_from_device(const uint32_t* w) {
   G1Xyzz p;
@@ -307,6 +325,14 @@ inline G2Xyzz g2_from_device(const uint32_t* w) {
   for (int i = 0; i < 8; i++) f[i] = fq_from_lazy(w + 12 * i);
   return p;
 }
+
+inline G1Xyzz g1_planes_horner(const uint32_t* planes, uint32_t nplanes, uint32_t chunk_log) {
+  return planes_horner_generic<G1Xyzz>(planes, 48, nplanes, chunk_log, g1_identity(), g1_from_device, g1_dbl, g1_add);
+}
+inline G2Xyzz g2_planes_horner(const uint32_t* planes, uint32_t nplanes, uint32_t chunk_log) {
+  return planes_horner_generic<G2Xyzz>(planes, 96, nplanes, chunk_log, g2_identity(), g2_from_device, g2_dbl, g2_add);
+}
+inline void g2_to_device_layout(const G2Xyzz& p, uint32_t* w) { std::memcpy(w, &p, sizeof(p)); }
 
 }  // namespace host
 }  // namespace b2z

@@ -106,9 +106,21 @@ void msm_run(Ctx* ctx, int slot, const MsmBases<C>& bases, const FrEl* d_scalars
 template <class C>
 void msm_sort(Ctx* ctx, int slot, const MsmBases<C>& bases, const FrEl* d_scalars_main, uint32_t n_main,
               const FrEl* d_scalars_tail, cudaStream_t st);
+//
+// `host_planes` (optional, pinned): the last, strictly serial step of the bucket reduction -- a Horner
+// pass of ~2 point operations per bit plane -- is then left to the CALLER's CPU, which does a point
+// operation in 0.5 us where a lone GPU warp needs 6 us: the bit-plane sums (nplanes XYZZ points, 2.5 KB
+// for G1) are copied to `host_planes->host` on `st` instead of reducing them into d_result, and the
+// caller finishes with host::planes_horner (host_fq.hpp) after synchronising.
+constexpr uint32_t kMsmMaxPlanes = 32;
+constexpr uint32_t kMsmChunkLog = 3;     // buckets per running-sum chunk = 8
+struct MsmHostPlanes {
+  void* host = nullptr;       // pinned, kMsmMaxPlanes * sizeof(Xyzz)
+  uint32_t nplanes = 0;       // set by msm_finish (0 = the sum is the identity)
+};
 template <class C>
 void msm_finish(Ctx* ctx, int slot, const MsmBases<C>& bases, typename C::Xyzz* d_result, cudaStream_t st,
-                cudaEvent_t wait_before_accum, cudaEvent_t record_after_accum);
+                cudaEvent_t wait_before_accum, cudaEvent_t record_after_accum, MsmHostPlanes* host_planes = nullptr);
 
 void msm_release_scratch(Ctx* ctx);
 

@@ -91,13 +91,14 @@ struct PkImpl {
   DevBuf<G1::Xyzz> g1_out;     // 0 A, 3 L, 4 H, 5 B1 (1, 2 unused: s*A and r*B1 are made on the host)
   DevBuf<G2::Xyzz> g2_out;     // B
   uint32_t* h_out = nullptr;   // pinned: B2Z_PARTIAL_BYTES
-  uint32_t* h_b1 = nullptr;    // pinned: B1 (input of the host-side r*B1)
+  uint32_t* h_planes = nullptr;   // pinned: bit-plane sums of the five MSMs (host-side Horner, msm.hpp)
+  MsmHostPlanes hp[5];            // 0 A, 1 B (G2), 2 B1, 3 L, 4 H
   cudaEvent_t ev_z = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_accum[4] = {nullptr, nullptr, nullptr, nullptr};
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
-    if (h_b1) cudaFreeHost(h_b1);
+    if (h_planes) cudaFreeHost(h_planes);
     if (ev_z) cudaEventDestroy(ev_z);
     for (auto& e : ev_done)
       if (e) cudaEventDestroy(e);
@@ -210,6 +211,7 @@ void fixed_base_entry(Ctx& c, const uint64_t* scalars, uint64_t n, uint64_t* out
 
 constexpr size_t kG1Bytes = sizeof(G1::Xyzz), kG2Bytes = sizeof(G2::Xyzz);
 constexpr size_t kPartialBytes = 5 * kG1Bytes + kG2Bytes;   // A | sA | rB1 | L | H | B
+constexpr size_t kPlaneSlotBytes = kMsmMaxPlanes * sizeof(G2::Xyzz);
 static_assert(kPartialBytes == B2Z_PARTIAL_BYTES, "header constant out of sync");
 
 // GPU part of a proof on this key (a whole key or one shard of it): leaves the XYZZ partial
@@ -257,27 +259,34 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
-  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3]);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 5 * kG1Bytes / 4, pk.g2_out.p, kG2Bytes, cudaMemcpyDeviceToHost, sB));
+  // every reduction stops at its bit-plane sums; the serial Horner pass over them runs on this thread
+  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3], &pk.hp[1]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
-  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, pk.ev_accum[3], pk.ev_accum[0]);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 0 * kG1Bytes / 4, g1o + 0, kG1Bytes, cudaMemcpyDeviceToHost, sA));
+  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, pk.ev_accum[3], pk.ev_accum[0], &pk.hp[0]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], sA));
-  msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, pk.ev_accum[0], pk.ev_accum[1]);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_b1, g1o + 5, kG1Bytes, cudaMemcpyDeviceToHost, sB1));
+  msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, pk.ev_accum[0], pk.ev_accum[1], &pk.hp[2]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], sB1));
-  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, pk.ev_accum[1], pk.ev_accum[2]);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 3 * kG1Bytes / 4, g1o + 3, kG1Bytes, cudaMemcpyDeviceToHost, sL));
+  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, pk.ev_accum[1], pk.ev_accum[2], &pk.hp[3]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], sL));
-  msm_finish<G1>(&c, 0, pk.h, g1o + 4, st, pk.ev_accum[2], nullptr);
-  B2Z_CUDA(cudaMemcpyAsync(pk.h_out + 4 * kG1Bytes / 4, g1o + 4, kG1Bytes, cudaMemcpyDeviceToHost, st));
-  // host: s*A and r*B1 while the GPU works on L and H
+  msm_finish<G1>(&c, 0, pk.h, g1o + 4, st, pk.ev_accum[2], nullptr, &pk.hp[4]);
+  auto g1_result = [&](int i) {
+    return host::g1_planes_horner(static_cast<const uint32_t*>(pk.hp[i].host), pk.hp[i].nplanes, kMsmChunkLog);
+  };
+  // host: A, s*A, B1, r*B1 while the GPU works on L and H
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[0]));
-  host::g1_to_device_layout(host::g1_mul_scalar(host::g1_from_device(pk.h_out), s_c.l), pk.h_out + 1 * kG1Bytes / 4);
+  const host::G1Xyzz A = g1_result(0);
+  host::g1_to_device_layout(A, pk.h_out + 0 * kG1Bytes / 4);
+  host::g1_to_device_layout(host::g1_mul_scalar(A, s_c.l), pk.h_out + 1 * kG1Bytes / 4);
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[2]));
-  host::g1_to_device_layout(host::g1_mul_scalar(host::g1_from_device(pk.h_b1), r_c.l), pk.h_out + 2 * kG1Bytes / 4);
-  for (auto& e : pk.ev_done) B2Z_CUDA(cudaEventSynchronize(e));
+  host::g1_to_device_layout(host::g1_mul_scalar(g1_result(2), r_c.l), pk.h_out + 2 * kG1Bytes / 4);
+  B2Z_CUDA(cudaEventSynchronize(pk.ev_done[1]));
+  host::g2_to_device_layout(
+      host::g2_planes_horner(static_cast<const uint32_t*>(pk.hp[1].host), pk.hp[1].nplanes, kMsmChunkLog),
+      pk.h_out + 5 * kG1Bytes / 4);
+  B2Z_CUDA(cudaEventSynchronize(pk.ev_done[3]));
+  host::g1_to_device_layout(g1_result(3), pk.h_out + 3 * kG1Bytes / 4);
   B2Z_CUDA(cudaStreamSynchronize(st));
+  host::g1_to_device_layout(g1_result(4), pk.h_out + 4 * kG1Bytes / 4);
   std::memcpy(partial_out, pk.h_out, kPartialBytes);
 }
 
@@ -460,7 +469,8 @@ b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank
     P.z.alloc(m); P.zc.alloc(P.ma ? P.ma : 1); P.tail.alloc(5);
     P.g1_out.alloc(6); P.g2_out.alloc(1);
     B2Z_CUDA(cudaMallocHost(&P.h_out, kPartialBytes));
-    B2Z_CUDA(cudaMallocHost(&P.h_b1, kG1Bytes));
+    B2Z_CUDA(cudaMallocHost(&P.h_planes, 5 * kPlaneSlotBytes));
+    for (int i = 0; i < 5; i++) P.hp[i].host = P.h_planes + (size_t)i * kPlaneSlotBytes / 4;
     B2Z_CUDA(cudaEventCreateWithFlags(&P.ev_z, cudaEventDisableTiming));
     for (auto& e : P.ev_done) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : P.ev_sorted) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
