@@ -396,7 +396,7 @@ def main():
             "peak_source": "b2z_measure_int_peak on this GPU, same run", "imad_32_peak": imad.value / 1e12},
         "launch_ms": acc_ms, "mixed_adds_per_launch": acc_adds, "launches_timed": int(cnt[G1ACC]),
     }
-    phase_names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "finalize"]
+    phase_names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
     phases = {nm: {"ms_per_step": ms[i] / args.steps, "launches_per_step": cnt[i] / args.steps,
                    "units_per_step": units[i] / args.steps} for i, nm in enumerate(phase_names)}
     ntt_el = units[0] / args.steps

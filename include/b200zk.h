@@ -190,7 +190,7 @@ B2Z_API b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, 
  *   0 NTT pass kernels (units: field elements)   1 witness-map pointwise (elements)
  *   2 MSM digits + counting sort (scalars)       3 MSM bucket accumulation G1 (mixed adds)
  *   4 MSM bucket accumulation G2 (mixed adds)    5 MSM partial lists / bucket reduction / combine
- *   6 proof finalisation (scalar muls, affine, serialization)                            */
+ *   6 constraint-row evaluation (CSR SpMV of A, B, C against z)                          */
 #define B2Z_PHASE_COUNT 8
 B2Z_API b2z_status b2z_profile_enable(b2z_ctx* ctx, int on);
 B2Z_API b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset);
@@ -201,6 +201,12 @@ B2Z_API uint64_t b2z_kernel_launches(const b2z_ctx* ctx);
 /* measured 32-bit multiply-add issue rates of the device (ops/s): plain IMAD and the
  * carry-chained 32x32+64 wide form the field arithmetic is built from               */
 B2Z_API b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
+
+/* Page-lock caller-owned host memory (cudaHostRegister) so that the per-proof upload of the assignment runs at
+ * PCIe speed instead of through the driver's staging buffer (61 MB of z at 2^22: ~1.2 ms instead of ~4 ms).  The
+ * caller keeps ownership; unregister before freeing.  A Rust caller registers the Vec<Fr> it reuses per request. */
+B2Z_API b2z_status b2z_host_register(b2z_ctx* ctx, void* ptr, uint64_t bytes);
+B2Z_API b2z_status b2z_host_unregister(b2z_ctx* ctx, void* ptr);
 
 /* ---- host-side self checks (no GPU needed) -------------------------------------------
  * The limb algorithms of the device code are written against a carry-flag

@@ -424,6 +424,26 @@ def test_prove_degenerate_shapes(b2z, ctx, codec, cpu_oracle, circuits):
     pk.free()
 
 
+def test_prove_from_page_locked_assignment(b2z, ctx, codec):
+    """b2z_host_register: the same proof bytes whether z is pageable or page-locked caller memory."""
+    import importlib
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    cm, z_int = fast.matrix_circuit_fast([[1, 2], [3, 4]], [[4, 3], [2, 1]])
+    rnd = random.Random(99)
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                      cm.num_variables, *[rnd.randrange(1, R) for _ in range(5)])
+    z = codec.fr_to_mont_limbs(z_int)
+    want = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, 21, 34)
+    zp = ctx.pin(z.copy())
+    got = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, zp, 21, 34)
+    ctx.unpin(zp)
+    assert got == want
+    with pytest.raises(b2z._ffi.B2zError):
+        ctx.unpin(zp)                       # not registered any more
+    cm.free()
+    pk.free()
+
+
 def test_prove_from_concurrent_host_threads(b2z, ctx, codec, circuits):
     """The reference serves proofs from several actix worker threads (src/main.rs:37).  Three host
     threads prove at the same time -- two with their own context and key copy, one sharing the session

@@ -40,7 +40,7 @@ pk, vk = b.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.
 t_keygen = time.time() - t0
 pk.upload(ctx, rank=rank, world=world)
 cm.upload(ctx)
-z = codec.fr_to_mont_limbs(z_int)
+z = ctx.pin(codec.fr_to_mont_limbs(z_int))      # page-locked: the 61 MB upload per proof runs at PCIe speed
 a, bb, c = b.LibsnarkReduction.constraint_evaluations_device(ctx, cm, z)
 r, s = rnd.randrange(R), rnd.randrange(R)
 

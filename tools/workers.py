@@ -13,7 +13,7 @@ inst = bench.build_instance(name)
 ctx0 = b.Context(0)
 pk0, vk = b.Groth16.generate_parameters_with_qap(ctx0, inst.cm, inst.num_constraints, inst.num_instance,
                                                  inst.num_variables, *bench.toxic_waste())
-z = b.codec.fr_to_mont_limbs(inst.z)
+z = ctx0.pin(b.codec.fr_to_mont_limbs(inst.z))
 want = b.Groth16.create_proof_with_matrices(ctx0, pk0, inst.cm, z, 5, 7)
 out = {}
 for W in range(1, max_w + 1):

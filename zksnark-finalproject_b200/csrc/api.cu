@@ -112,6 +112,20 @@ b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double* imad_w
   });
 }
 
+b2z_status b2z_host_register(b2z_ctx* ctx, void* ptr, uint64_t bytes) {
+  return guarded(ctx, [&](Ctx&) {
+    B2Z_REQUIRE(ptr != nullptr && bytes > 0, B2Z_EINVAL, "b2z_host_register: empty range");
+    B2Z_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  });
+}
+
+b2z_status b2z_host_unregister(b2z_ctx* ctx, void* ptr) {
+  return guarded(ctx, [&](Ctx&) {
+    B2Z_REQUIRE(ptr != nullptr, B2Z_EINVAL, "b2z_host_unregister: NULL");
+    B2Z_CUDA(cudaHostUnregister(ptr));
+  });
+}
+
 const char* b2z_last_error(const b2z_ctx* ctx) { return ctx ? ctx->impl.last_error.c_str() : "null context"; }
 
 b2z_status b2z_ntt_fr(b2z_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse, const uint64_t coset_gen[4]) {

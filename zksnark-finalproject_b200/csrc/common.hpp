@@ -87,7 +87,7 @@ enum Phase {
   PH_MSM_ACCUM_G1 = 3,  // bucket accumulation kernel, G1   units: mixed additions
   PH_MSM_ACCUM_G2 = 4,  // bucket accumulation kernel, G2   units: mixed additions
   PH_MSM_REDUCE = 5,    // partial lists, bucket reduction, window combine
-  PH_FINALIZE = 6,      // scalar muls, final sums, affine + serialization
+  PH_R1CS_EVAL = 6,     // constraint-row evaluation (CSR SpMV)
   PH_COUNT = 8
 };
 

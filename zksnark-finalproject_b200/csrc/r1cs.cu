@@ -95,6 +95,7 @@ void upload_csr(CsrDev& d, const uint64_t* row_ptr, const uint32_t* cols, const 
 
 void eval_rows(Ctx& c, R1csImpl& R, const FrEl* d_z, FrEl* a, FrEl* b, FrEl* cc, cudaStream_t st) {
   const size_t n = (size_t)1 << R.log_n;
+  ProfileScope ps(&c, PH_R1CS_EVAL, st, 3 * (R.nc + R.l));
   B2Z_CUDA(cudaMemsetAsync(a, 0, n * sizeof(FrEl), st));
   B2Z_CUDA(cudaMemsetAsync(b, 0, n * sizeof(FrEl), st));
   B2Z_CUDA(cudaMemsetAsync(cc, 0, n * sizeof(FrEl), st));

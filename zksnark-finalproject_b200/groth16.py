@@ -60,6 +60,16 @@ class Context:
         self.handle = h
         self.device = device
 
+    def pin(self, arr):
+        """b2z_host_register: page-lock a (contiguous, caller-owned) numpy array that is uploaded per proof,
+        e.g. the assignment z.  Returns the array; unpin() before it is garbage-collected."""
+        arr = np.ascontiguousarray(arr)
+        self.check(self._lib.b2z_host_register(self.handle, _ptr(arr), arr.nbytes))
+        return arr
+
+    def unpin(self, arr):
+        self.check(self._lib.b2z_host_unregister(self.handle, _ptr(arr)))
+
     def check(self, st):
         if st == _ffi.B2Z_OK:
             return
