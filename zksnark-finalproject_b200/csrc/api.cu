@@ -115,7 +115,7 @@ b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double* imad_w
 b2z_status b2z_host_register(b2z_ctx* ctx, void* ptr, uint64_t bytes) {
   return guarded(ctx, [&](Ctx&) {
     B2Z_REQUIRE(ptr != nullptr && bytes > 0, B2Z_EINVAL, "b2z_host_register: empty range");
-    B2Z_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    B2Z_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
   });
 }
 
