@@ -398,6 +398,41 @@ def test_prove_point_sharded_equals_whole_key(b2z, ctx, codec, circuits, world):
     pk.free()
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_prove_sharded_with_distributed_witness_map(b2z, ctx, codec, world):
+    """b2z_groth16_shard_begin / b2z_r1cs_coset_evals / b2z_groth16_shard_finish: every shard gets the three
+    coset evaluation vectors from "somewhere" (here: computed once on this GPU into torch buffers, as rank
+    j would before broadcasting them) and the combined proof equals the whole-key proof."""
+    import importlib
+    import torch
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    A = [[(5 * i + j + 1) for j in range(3)] for i in range(3)]
+    B = [[(i + 2 * j + 3) for j in range(3)] for i in range(3)]
+    cm, z_int = fast.matrix_circuit_fast(A, B)
+    rnd = random.Random(31 + world)
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                      cm.num_variables, *[rnd.randrange(1, R) for _ in range(5)])
+    z = codec.fr_to_mont_limbs(z_int)
+    r, s = rnd.randrange(R), rnd.randrange(R)
+    want = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r, s)
+    parts = []
+    for k in range(world):
+        shard = b2z.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                               pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                               pk.beta_g2, pk.delta_g2).upload(ctx, rank=k, world=world)
+        bufs = [torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+        keep = b2z.Groth16.shard_begin(ctx, shard, cm, z, r, s)
+        for j in range(3):
+            b2z.Groth16.coset_evals(ctx, cm, j, bufs[j].data_ptr())
+        torch.cuda.synchronize()
+        parts.append(b2z.Groth16.shard_finish(ctx, shard, *(t.data_ptr() for t in bufs)))
+        del keep
+        shard.free()
+    assert b2z.Groth16.combine(parts) == want
+    cm.free()
+    pk.free()
+
+
 def test_prove_degenerate_shapes(b2z, ctx, codec, cpu_oracle, circuits):
     """Edge shapes: a system with a single witness and nearly empty rows (Fibonacci, 0 steps: one
     constraint, domain 8), more shards than variables, and an all-zero witness vector."""

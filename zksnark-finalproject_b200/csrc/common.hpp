@@ -135,6 +135,9 @@ void measure_int_peak(Ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
 // Full witness map on device buffers a, b, c (natural order, destroyed); h is
 // left in `a`, in bit-reversed order if !natural_out.
 void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st);
+// its two halves (the first one per input vector), for the distributed witness map of the sharded prover
+void witness_map_transform(Ctx* ctx, FrEl* x, uint32_t log_n, cudaStream_t st);
+void witness_map_quotient(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // Context

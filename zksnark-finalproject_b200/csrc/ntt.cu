@@ -430,18 +430,30 @@ const FrEl* ntt_twiddles(Ctx* ctx, uint32_t log_n, TwKind kind, cudaStream_t st)
 //                                     - NTT_coset(iNTT c)) / Z_H(g) )
 // All n^-1 factors and Z^-1 are folded into wm_k1, wm_k2.
 // ---------------------------------------------------------------------------
-void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st) {
-  const NttDomain& d = ntt_domain(ctx, log_n);
+// One input vector: evaluations on the domain -> evaluations on the coset g H (unscaled inverse
+// transform fused with the coset transform; the n^-1 factors are folded into the pointwise constants).
+void witness_map_transform(Ctx* ctx, FrEl* x, uint32_t log_n, cudaStream_t st) {
   const FrEl* tw_inv = ntt_twiddles(ctx, log_n, TW_INV, st);
   const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
+  ntt_dif_dit(ctx, tw_inv, tw_cf, x, log_n, st);
+}
+
+// a <- coefficients of (a b - c) / Z_H from the three coset evaluation vectors.
+void witness_map_quotient(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, bool natural_out,
+                          cudaStream_t st) {
+  const NttDomain& d = ntt_domain(ctx, log_n);
   const FrEl* tw_ci = ntt_twiddles(ctx, log_n, TW_COSET_INV, st);
-  ntt_dif_dit(ctx, tw_inv, tw_cf, a, log_n, st);
-  ntt_dif_dit(ctx, tw_inv, tw_cf, b, log_n, st);
-  ntt_dif_dit(ctx, tw_inv, tw_cf, c, log_n, st);
   wm_pointwise(ctx, a, b, c, log_n, d.wm_k1, d.wm_k2, st);
   ntt_dif(ctx, tw_ci, a, log_n, st);
   if (natural_out) ntt_bitrev(ctx, a, log_n, nullptr, nullptr, nullptr, st);
   else fr_canonicalize(ctx, a, (size_t)1 << log_n, st);
+}
+
+void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st) {
+  witness_map_transform(ctx, a, log_n, st);
+  witness_map_transform(ctx, b, log_n, st);
+  witness_map_transform(ctx, c, log_n, st);
+  witness_map_quotient(ctx, a, b, c, log_n, natural_out, st);
 }
 
 // ---------------------------------------------------------------------------

@@ -93,6 +93,7 @@ struct PkImpl {
   uint32_t* h_out = nullptr;   // pinned: B2Z_PARTIAL_BYTES
   uint32_t* h_planes = nullptr;   // pinned: bit-plane sums of the five MSMs (host-side Horner, msm.hpp)
   MsmHostPlanes hp[5];            // 0 A, 1 B (G2), 2 B1, 3 L, 4 H
+  FrEl r_c, s_c;                  // the proof's r, s as canonical integers (prove_begin -> prove_end)
   cudaEvent_t ev_z = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_accum[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -216,23 +217,27 @@ static_assert(kPartialBytes == B2Z_PARTIAL_BYTES, "header constant out of sync")
 
 // GPU part of a proof on this key (a whole key or one shard of it): leaves the XYZZ partial
 // sums A, s*A, r*B1, L, H (G1) and B (G2) in partial_out (host memory).
-void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
-                          const uint64_t s[4], uint8_t* partial_out) {
-  cudaStream_t st = c.stream;
+// A proof in three steps that share the key's scratch (PkImpl): prove_begin launches everything that
+// depends on z only, prove_quotient what needs the three coset evaluation vectors, prove_end waits and
+// does the host epilogue.  The single-GPU prover runs them back to back; the sharded prover with a
+// distributed witness map (b2z_groth16_shard_*) lets the caller exchange the coset evaluations between
+// prove_begin and prove_quotient while the z-only accumulations are already running.
+void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
   cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
   // host-side scalars: r, s, -(r s) as canonical integers
   const FrEl r_m = Fr::reduce(fr_load_host(r)), s_m = Fr::reduce(fr_load_host(s));
-  const FrEl r_c = Fr::from_mont(r_m), s_c = Fr::from_mont(s_m);
+  pk.r_c = Fr::from_mont(r_m);
+  pk.s_c = Fr::from_mont(s_m);
   const FrEl neg_rs = Fr::from_mont(Fr::reduce(Fr::neg(Fr::reduce(Fr::mul(r_m, s_m)))));
   FrEl one_c = Fr::zero();
   one_c.l[0] = 1;
-  const FrEl tail_h[5] = {one_c, r_c, one_c, s_c, neg_rs};      // A: {1, r}; B1, B: {1, s}; L: {-rs}
+  const FrEl tail_h[5] = {one_c, pk.r_c, one_c, pk.s_c, neg_rs};      // A: {1, r}; B1, B: {1, s}; L: {-rs}
   B2Z_CUDA(cudaMemcpyAsync(pk.tail.p, tail_h, sizeof(tail_h), cudaMemcpyHostToDevice, sA));
   fr_from_mont_device(&c, d_z + pk.lo, pk.zc.p, pk.ma, sA);     // this shard's slice of z as canonical integers
   B2Z_CUDA(cudaEventRecord(pk.ev_z, sA));
-  G1::Xyzz* g1o = pk.g1_out.p;   // 0 A, 1 sA, 2 rB1, 3 L, 4 H, 5 B1
+  G1::Xyzz* g1o = pk.g1_out.p;   // 0 A, 3 L, 4 H, 5 B1
   const FrEl* z_l = pk.zc.p + (pk.l_lo - pk.lo);
-  // ---- light phase: every sort and the witness map, concurrently
+  // ---- the four z-only sorts, concurrently
   msm_sort<G1>(&c, 1, pk.a_set, pk.zc.p, pk.ma, pk.tail.p + 0, sA);
   B2Z_CUDA(cudaEventRecord(pk.ev_sorted[0], sA));
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_z, 0));
@@ -244,22 +249,18 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   B2Z_CUDA(cudaStreamWaitEvent(sL, pk.ev_z, 0));
   msm_sort<G1>(&c, 4, pk.l_set, z_l, pk.ml, pk.tail.p + 4, sL);
   B2Z_CUDA(cudaEventRecord(pk.ev_sorted[3], sL));
-  witness_map_device(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);    // whole domain, every shard
-  fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
-  msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);
-  // ---- heavy phase: B -> A -> B1 -> L -> H, accumulations chained by events.
+  // ---- accumulations B -> A -> B1 -> L (-> H in prove_quotient), chained by events.
   // The G2 accumulation (255 registers: it fills every SM, nothing can be scheduled beside it) goes
   // first, right after the z-only sorts, so that its tail -- the longest -- hides under the G1
   // accumulations.  A G1 accumulation leaves room on every SM for sort / NTT / tail blocks (the tail
   // kernels are register-capped for exactly that), so the witness map and the other tails overlap too.
-  // s*A and r*B1 are computed by the HOST as soon as A and B1 arrive (0.2 ms each), while the GPU is
-  // still busy with L and H.  (With the scalar multiplications on the GPU -- 1.5 ms each even with
-  // lane-cooperative arithmetic -- every order tried put one of them on the critical path: 7.65-8.3 ms
-  // per C2 proof.)
+  // Every reduction stops at its bit-plane sums; the serial Horner pass over them, s*A and r*B1 are done
+  // by the HOST (prove_end) while the GPU is still busy with L and H.  (With the scalar multiplications
+  // on the GPU -- 1.5 ms each even with lane-cooperative arithmetic -- every order tried put one of them
+  // on the critical path: 7.65-8.3 ms per C2 proof.)
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
   B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
-  // every reduction stops at its bit-plane sums; the serial Horner pass over them runs on this thread
   msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3], &pk.hp[1]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
   msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, pk.ev_accum[3], pk.ev_accum[0], &pk.hp[0]);
@@ -268,26 +269,47 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], sB1));
   msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, pk.ev_accum[1], pk.ev_accum[2], &pk.hp[3]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], sL));
-  msm_finish<G1>(&c, 0, pk.h, g1o + 4, st, pk.ev_accum[2], nullptr, &pk.hp[4]);
+}
+
+// d_a, d_b, d_c: evaluations of the three QAP combinations on the coset g H (d_a is clobbered)
+void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c) {
+  cudaStream_t st = c.stream;
+  witness_map_quotient(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);    // whole domain, every shard
+  fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
+  msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);
+  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, st, pk.ev_accum[2], nullptr, &pk.hp[4]);
+}
+
+void prove_end(Ctx& c, PkImpl& pk, uint8_t* partial_out) {
   auto g1_result = [&](int i) {
     return host::g1_planes_horner(static_cast<const uint32_t*>(pk.hp[i].host), pk.hp[i].nplanes, kMsmChunkLog);
   };
-  // host: A, s*A, B1, r*B1 while the GPU works on L and H
+  // A, s*A, B1, r*B1 while the GPU works on L and H
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[0]));
   const host::G1Xyzz A = g1_result(0);
   host::g1_to_device_layout(A, pk.h_out + 0 * kG1Bytes / 4);
-  host::g1_to_device_layout(host::g1_mul_scalar(A, s_c.l), pk.h_out + 1 * kG1Bytes / 4);
+  host::g1_to_device_layout(host::g1_mul_scalar(A, pk.s_c.l), pk.h_out + 1 * kG1Bytes / 4);
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[2]));
-  host::g1_to_device_layout(host::g1_mul_scalar(g1_result(2), r_c.l), pk.h_out + 2 * kG1Bytes / 4);
+  host::g1_to_device_layout(host::g1_mul_scalar(g1_result(2), pk.r_c.l), pk.h_out + 2 * kG1Bytes / 4);
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[1]));
   host::g2_to_device_layout(
       host::g2_planes_horner(static_cast<const uint32_t*>(pk.hp[1].host), pk.hp[1].nplanes, kMsmChunkLog),
       pk.h_out + 5 * kG1Bytes / 4);
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[3]));
   host::g1_to_device_layout(g1_result(3), pk.h_out + 3 * kG1Bytes / 4);
-  B2Z_CUDA(cudaStreamSynchronize(st));
+  B2Z_CUDA(cudaStreamSynchronize(c.stream));
   host::g1_to_device_layout(g1_result(4), pk.h_out + 4 * kG1Bytes / 4);
   std::memcpy(partial_out, pk.h_out, kPartialBytes);
+}
+
+void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
+                          const uint64_t s[4], uint8_t* partial_out) {
+  prove_begin(c, pk, d_z, r, s);
+  witness_map_transform(&c, d_a, pk.log_n, c.stream);
+  witness_map_transform(&c, d_b, pk.log_n, c.stream);
+  witness_map_transform(&c, d_c, pk.log_n, c.stream);
+  prove_quotient(c, pk, d_a, d_b, d_c);
+  prove_end(c, pk, partial_out);
 }
 
 // Host epilogue: sum the partials of all shards, normalise, serialise (host_fq.hpp).
@@ -338,6 +360,14 @@ void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrE
 void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
                                      const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out) {
   prove_partial_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, partial_out);
+}
+void prove_begin_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
+  prove_begin(c, const_cast<b2z_pk*>(pk)->impl, d_z, r, s);
+}
+void prove_finish_on(Ctx& c, const b2z_pk* pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, uint8_t* partial_out) {
+  PkImpl& P = const_cast<b2z_pk*>(pk)->impl;
+  prove_quotient(c, P, d_a, d_b, d_c);
+  prove_end(c, P, partial_out);
 }
 }  // namespace b2z
 

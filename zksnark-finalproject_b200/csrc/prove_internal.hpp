@@ -12,4 +12,8 @@ void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrE
 // the same for one shard of a key: B2Z_PARTIAL_BYTES of partial sums
 void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
                                      const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);
+// the same in two calls (sharded prover with a distributed witness map): z-only work first (returns while the
+// GPU is busy), then quotient + H + host epilogue from the three COSET evaluation vectors (d_a is clobbered)
+void prove_begin_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]);
+void prove_finish_on(Ctx& c, const b2z_pk* pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, uint8_t* partial_out);
 }  // namespace b2z

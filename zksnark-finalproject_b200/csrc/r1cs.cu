@@ -23,6 +23,10 @@ struct R1csImpl {
   uint32_t log_n = 0;
   CsrDev mat[3];
   DevBuf<FrEl> z, ea, eb, ec;
+  cudaEvent_t ev_z = nullptr;      // z uploaded (b2z_groth16_shard_begin -> b2z_r1cs_coset_evals)
+  ~R1csImpl() {
+    if (ev_z) cudaEventDestroy(ev_z);
+  }
 };
 
 namespace {
@@ -107,6 +111,22 @@ void eval_rows(Ctx& c, R1csImpl& R, const FrEl* d_z, FrEl* a, FrEl* b, FrEl* cc,
   B2Z_LAUNCHED(&c);
 }
 
+// rows of ONE matrix (0 = A with the instance rows appended, 1 = B, 2 = C) against z, zero-padded to the domain
+void eval_one(Ctx& c, R1csImpl& R, uint32_t which, const FrEl* d_z, FrEl* out, cudaStream_t st) {
+  const size_t n = (size_t)1 << R.log_n;
+  ProfileScope ps(&c, PH_R1CS_EVAL, st, R.nc + (which == 0 ? R.l : 0));
+  B2Z_CUDA(cudaMemsetAsync(out, 0, n * sizeof(FrEl), st));
+  if (R.nc) {
+    spmv_kernel<<<(uint32_t)((R.nc + 127) / 128), 128, 0, st>>>(R.mat[which].row_ptr.p, R.mat[which].cols.p,
+                                                              R.mat[which].coeffs.p, d_z, (uint32_t)R.nc, out);
+    B2Z_LAUNCHED(&c);
+  }
+  if (which == 0) {
+    B2Z_CUDA(cudaMemcpyAsync(out + R.nc, d_z, R.l * sizeof(FrEl), cudaMemcpyDeviceToDevice, st));
+    fr_canonicalize(&c, out + R.nc, R.l, st);
+  }
+}
+
 }  // namespace
 }  // namespace b2z
 
@@ -138,6 +158,7 @@ b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_
     upload_csr(R.mat[2], c_row_ptr, c_cols, c_coeffs, num_constraints, num_variables, c.stream);
     const size_t n = (size_t)1 << log_n;
     R.z.alloc(num_variables); R.ea.alloc(n); R.eb.alloc(n); R.ec.alloc(n);
+    B2Z_CUDA(cudaEventCreateWithFlags(&R.ev_z, cudaEventDisableTiming));
     *out = r.release();
   });
 }
@@ -234,6 +255,41 @@ b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
     eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, c.stream);
     prove_partial_on_device_buffers(c, pk, R.ea.p, R.eb.p, R.ec.p, R.z.p, rr, ss, partial_out);
     cudaEventDestroy(ev);
+  });
+}
+
+// ---- point-sharded proof with a distributed witness map (include/b200zk.h) ----
+b2z_status b2z_groth16_shard_begin(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, const uint64_t* z, const uint64_t rr[4],
+                                   const uint64_t ss[4]) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk && r && z && rr && ss, B2Z_EINVAL, "b2z_groth16_shard_begin: NULL argument");
+    R1csImpl& R = r->impl;
+    B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_shard_begin: key and matrices disagree");
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
+    prove_begin_on(c, pk, R.z.p, rr, ss);
+  });
+}
+
+b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r, uint32_t which, uint64_t* d_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(r && d_out && which < 3, B2Z_EINVAL, "b2z_r1cs_coset_evals: bad argument");
+    R1csImpl& R = r->impl;
+    cudaStream_t st = c.stream;
+    B2Z_CUDA(cudaStreamWaitEvent(st, R.ev_z, 0));
+    FrEl* out = reinterpret_cast<FrEl*>(d_out);
+    eval_one(c, R, which, R.z.p, out, st);
+    witness_map_transform(&c, out, R.log_n, st);
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+b2z_status b2z_groth16_shard_finish(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_a, const uint64_t* d_b,
+                                    const uint64_t* d_c, uint8_t* partial_out) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk && d_a && d_b && d_c && partial_out, B2Z_EINVAL, "b2z_groth16_shard_finish: NULL argument");
+    prove_finish_on(c, pk, reinterpret_cast<FrEl*>(d_a), reinterpret_cast<const FrEl*>(d_b),
+                    reinterpret_cast<const FrEl*>(d_c), partial_out);
   });
 }
 

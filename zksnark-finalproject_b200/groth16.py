@@ -588,6 +588,58 @@ class Groth16:
         return Groth16.combine([bytes(x.cpu().numpy().tobytes()) for x in parts])
 
     @staticmethod
+    def shard_begin(ctx, pk, cm, full_assignment, r, s):
+        """b2z_groth16_shard_begin: upload z, start the z-only part of this shard (asynchronous)."""
+        cm.upload(ctx)
+        z = _fr_array(full_assignment)
+        rs = codec.fr_to_mont_limbs([r, s])
+        ctx.check(ctx._lib.b2z_groth16_shard_begin(ctx.handle, pk._handle, cm._handle, _ptr(z), _ptr(rs[0:1]),
+                                                   _ptr(rs[1:2])))
+        return z           # keep alive until shard_finish
+
+    @staticmethod
+    def coset_evals(ctx, cm, which, device_ptr):
+        """b2z_r1cs_coset_evals: matrix `which` (0 A, 1 B, 2 C) against the z of shard_begin, transformed to the
+        coset, into a caller-owned device buffer (domain_size x 32 bytes)."""
+        ctx.check(ctx._lib.b2z_r1cs_coset_evals(ctx.handle, cm._handle, int(which), ctypes.c_void_p(int(device_ptr))))
+
+    @staticmethod
+    def shard_finish(ctx, pk, d_a, d_b, d_c):
+        """b2z_groth16_shard_finish from three device pointers -> this shard's B2Z_PARTIAL_BYTES."""
+        out = np.zeros(_ffi.PARTIAL_BYTES, dtype=np.uint8)
+        ctx.check(ctx._lib.b2z_groth16_shard_finish(ctx.handle, pk._handle, ctypes.c_void_p(int(d_a)),
+                                                    ctypes.c_void_p(int(d_b)), ctypes.c_void_p(int(d_c)), _ptr(out)))
+        return out.tobytes()
+
+    @staticmethod
+    def create_proof_sharded_distributed(ctx, pk, cm, full_assignment, r, s, group=None, buffers=None):
+        """create_proof_sharded with the witness map's three input transforms done ONCE in the group instead of
+        once per rank: rank j % world evaluates and transforms matrix j, the coset evaluations are broadcast
+        over NCCL (3 x domain_size x 32 bytes) while every rank's z-only accumulations are already running.
+        `buffers`: three torch CUDA int64 tensors of shape (domain_size, 4) to reuse across proofs."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        if buffers is None:
+            buffers = [torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+        keep = Groth16.shard_begin(ctx, pk, cm, full_assignment, r, s)
+        owners = [j % world for j in range(3)]
+        for j in range(3):
+            if owners[j] == rank:
+                Groth16.coset_evals(ctx, cm, j, buffers[j].data_ptr())
+        works = [dist.broadcast(buffers[j], src=dist.get_global_rank(group, owners[j]) if group is not None else owners[j],
+                                group=group, async_op=True) for j in range(3)]
+        for w in works:
+            w.wait()
+        torch.cuda.current_stream().synchronize()      # the library works on its own streams
+        mine = Groth16.shard_finish(ctx, pk, buffers[0].data_ptr(), buffers[1].data_ptr(), buffers[2].data_ptr())
+        del keep
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        return Groth16.combine([bytes(x.cpu().numpy().tobytes()) for x in parts])
+
+    @staticmethod
     def create_random_proof_with_reduction(ctx, pk, matrices, num_constraints, full_assignment_ints, rng):
         """Draws r then s from `rng` (a callable returning canonical Fr ints, in the
         order ark-groth16 draws them), evaluates the constraint rows on the host and proves."""
