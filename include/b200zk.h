@@ -205,20 +205,24 @@ B2Z_API b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double
 /* ---- Point-sharded proof with a DISTRIBUTED witness map -------------------------------------
  * With b2z_groth16_prove_partial every shard repeats the whole witness map (8.4 of the 25 ms a shard-of-8 takes
  * at 2^22).  Here the three input transforms are done once per box:
- *   1. every rank:        b2z_groth16_shard_begin(ctx, pk_shard, r1cs, z, r, s)
- *        uploads z and starts everything that depends on z only (four sorts, the B2 / A / B1 / L accumulations);
- *        returns while the GPU is busy;
- *   2. rank j in {0,1,2}: b2z_r1cs_coset_evals(ctx, r1cs, j, d_out)
+ *   - every rank:        b2z_groth16_shard_begin(ctx, pk_shard, r1cs, z, r, s)
+ *        starts everything that depends on z only (four sorts, the B2 / A / B1 / L accumulations) and returns
+ *        while the GPU is busy;
+ *   - rank j in {0,1,2}: b2z_r1cs_coset_evals(ctx, r1cs, j, z, d_out)
  *        rows of matrix j (0 = A, 1 = B, 2 = C) against z, then inverse transform + coset transform, into a
  *        caller-owned DEVICE buffer of 2^log_n x 32 bytes; returns when d_out is complete.  The caller sends it to
- *        the other ranks (NCCL broadcast, peer copy ...): the library links no communication runtime;
- *   3. every rank:        b2z_groth16_shard_finish(ctx, pk_shard, d_a, d_b, d_c, partial_out)
+ *        the other ranks (NCCL broadcast, peer copy ...): the library links no communication runtime.  An owner
+ *        should call this BEFORE shard_begin -- the accumulations fill the GPU and would starve the transform
+ *        every other rank is waiting for;
+ *   - every rank:        b2z_groth16_shard_finish(ctx, pk_shard, d_a, d_b, d_c, partial_out)
  *        pointwise quotient, last transform, this shard's H sum, host epilogue: B2Z_PARTIAL_BYTES as from
  *        b2z_groth16_prove_partial (d_a is clobbered).  Combine with b2z_groth16_combine.
- * A rank must not start another proof on the same key between 1 and 3.                                         */
+ * z: the assignment in host memory for the FIRST of these calls of a proof (it is uploaded once), NULL afterwards.
+ * A rank must not start another proof on the same key / r1cs before shard_finish.                               */
 B2Z_API b2z_status b2z_groth16_shard_begin(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r1cs, const uint64_t* z,
                                            const uint64_t r[4], const uint64_t s[4]);
-B2Z_API b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r1cs, uint32_t which, uint64_t* d_out);
+B2Z_API b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r1cs, uint32_t which, const uint64_t* z,
+                                        uint64_t* d_out);
 B2Z_API b2z_status b2z_groth16_shard_finish(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_a, const uint64_t* d_b,
                                             const uint64_t* d_c, uint8_t* partial_out);
 

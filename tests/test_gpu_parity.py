@@ -421,9 +421,14 @@ def test_prove_sharded_with_distributed_witness_map(b2z, ctx, codec, world):
                                pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
                                pk.beta_g2, pk.delta_g2).upload(ctx, rank=k, world=world)
         bufs = [torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
-        keep = b2z.Groth16.shard_begin(ctx, shard, cm, z, r, s)
-        for j in range(3):
-            b2z.Groth16.coset_evals(ctx, cm, j, bufs[j].data_ptr())
+        if k % 2 == 0:       # either call may come first; the first one carries z
+            keep = b2z.Groth16.shard_begin(ctx, shard, cm, z, r, s)
+            for j in range(3):
+                b2z.Groth16.coset_evals(ctx, cm, j, bufs[j].data_ptr())
+        else:
+            for j in range(3):
+                b2z.Groth16.coset_evals(ctx, cm, j, bufs[j].data_ptr(), z if j == 0 else None)
+            keep = b2z.Groth16.shard_begin(ctx, shard, cm, None, r, s)
         torch.cuda.synchronize()
         parts.append(b2z.Groth16.shard_finish(ctx, shard, *(t.data_ptr() for t in bufs)))
         del keep

@@ -16,6 +16,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=8)
 ap.add_argument("--size", type=int, default=64)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--distributed-wm", action="store_true",
+                help="GPUs 0..2 transform a, b, c once and push the coset evaluations to their peers (copy engines)")
 args = ap.parse_args()
 codec = b.codec
 R = codec.R_MOD
@@ -48,6 +50,12 @@ z = ctxs[0].pin(codec.fr_to_mont_limbs(z_int))
 r, s = rnd.randrange(R), rnd.randrange(R)
 parts = [None] * G
 go = [threading.Semaphore(0) for _ in range(G)]
+if args.distributed_wm:
+    import torch
+    # bufs[k][j]: coset evaluations of matrix j on device k
+    bufs = [[torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda:%d" % k) for _ in range(3)] for k in range(G)]
+    ready = [threading.Event() for _ in range(3)]
+    owners = [j % G for j in range(3)]
 done = threading.Semaphore(0)
 stop = False
 
@@ -57,7 +65,27 @@ def worker(k):
         go[k].acquire()
         if stop:
             return
-        parts[k] = b.Groth16.create_proof_partial_with_matrices(ctxs[k], shards[k], cms[k], z, r, s)
+        if args.distributed_wm:
+            uploaded = False
+            for j in range(3):
+                if owners[j] == k:          # transform first: the accumulations would starve it
+                    b.Groth16.coset_evals(ctxs[k], cms[k], j, bufs[k][j].data_ptr(), None if uploaded else z)
+                    uploaded = True
+                    with torch.cuda.device(k):
+                        for peer in range(G):
+                            if peer != k:   # peer-to-peer DMA: needs no SM on either side
+                                bufs[peer][j].copy_(bufs[k][j], non_blocking=True)
+            keep = b.Groth16.shard_begin(ctxs[k], shards[k], cms[k], None if uploaded else z, r, s)
+            if uploaded:
+                torch.cuda.synchronize(k)
+                for j in range(3):
+                    if owners[j] == k:
+                        ready[j].set()
+            for j in range(3):
+                ready[j].wait()
+            parts[k] = b.Groth16.shard_finish(ctxs[k], shards[k], *(t.data_ptr() for t in bufs[k]))
+        else:
+            parts[k] = b.Groth16.create_proof_partial_with_matrices(ctxs[k], shards[k], cms[k], z, r, s)
         done.release()
 
 
@@ -66,6 +94,9 @@ workers = [threading.Thread(target=worker, args=(k,), daemon=True) for k in rang
 
 
 def step():
+    if args.distributed_wm:
+        for e in ready:
+            e.clear()
     for k in range(G):
         go[k].release()
     for _ in range(G):
@@ -94,11 +125,12 @@ v.alpha_g1 = codec.g1_from_limbs(vk.alpha_g1.reshape(1, -1))[0]
 v.beta_g2, v.gamma_g2, v.delta_g2 = (codec.g2_from_limbs(x.reshape(1, -1))[0] for x in (vk.beta_g2, vk.gamma_g2, vk.delta_g2))
 v.gamma_abc_g1 = codec.g1_from_limbs(*vk.gamma_abc_g1)
 ok = OG.verify(v, z_int[1:cm.num_instance_variables], O.proof_deserialize_compressed(proof))
-line = {"mode": "point-sharded single proof, one process, one host thread per GPU", "n_gpus": G,
+line = {"mode": "point-sharded single proof, one process, one host thread per GPU"
+                + (", distributed witness map (peer copies)" if args.distributed_wm else ""), "n_gpus": G,
         "workload": "matrix %dx%d" % (n, n), "num_constraints": cm.num_constraints, "domain": cm.domain_size,
         "ms_per_proof_wall": wall * 1e3, "proof_verifies": bool(ok), "keygen_s": t_keygen,
         "collective": "none (host sum of %d B per GPU)" % b._ffi.PARTIAL_BYTES,
         "inputs": "z in page-locked host memory (H2D to every GPU inside the timed region); rows evaluated on the GPU"}
 print(json.dumps(line))
 os.makedirs("gpurun_out", exist_ok=True)
-open("gpurun_out/sharded_threads_%d_%d.json" % (n, G), "w").write(json.dumps(line) + "\n")
+open("gpurun_out/sharded_threads%s_%d_%d.json" % ("_dwm" if args.distributed_wm else "", n, G), "w").write(json.dumps(line) + "\n")

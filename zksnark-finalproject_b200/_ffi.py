@@ -59,7 +59,7 @@ SIGNATURES = {
     "b2z_kernel_launches": (ctypes.c_uint64, [vp]),
     "b2z_measure_int_peak": (ctypes.c_int32, [vp, vp, vp]),
     "b2z_groth16_shard_begin": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp]),
-    "b2z_r1cs_coset_evals": (ctypes.c_int32, [vp, vp, ctypes.c_uint32, vp]),
+    "b2z_r1cs_coset_evals": (ctypes.c_int32, [vp, vp, ctypes.c_uint32, vp, vp]),
     "b2z_groth16_shard_finish": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp]),
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),

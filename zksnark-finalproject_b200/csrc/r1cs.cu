@@ -23,7 +23,8 @@ struct R1csImpl {
   uint32_t log_n = 0;
   CsrDev mat[3];
   DevBuf<FrEl> z, ea, eb, ec;
-  cudaEvent_t ev_z = nullptr;      // z uploaded (b2z_groth16_shard_begin -> b2z_r1cs_coset_evals)
+  cudaEvent_t ev_z = nullptr;      // z uploaded (b2z_groth16_shard_begin / b2z_r1cs_coset_evals, whichever came first)
+  bool z_valid = false;
   ~R1csImpl() {
     if (ev_z) cudaEventDestroy(ev_z);
   }
@@ -259,22 +260,36 @@ b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
 }
 
 // ---- point-sharded proof with a distributed witness map (include/b200zk.h) ----
+namespace {
+// z != NULL: upload the assignment (aux stream 0, where the MSM scalars are prepared) and mark it;
+// z == NULL: reuse the one uploaded by the previous shard call on this r1cs
+void shard_assignment(Ctx& c, R1csImpl& R, const uint64_t* z, const char* who) {
+  if (z != nullptr) {
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
+    R.z_valid = true;
+  }
+  if (!R.z_valid) throw StatusError{B2Z_EINVAL, std::string(who) + ": no assignment uploaded yet (z is NULL)"};
+}
+}  // namespace
+
 b2z_status b2z_groth16_shard_begin(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, const uint64_t* z, const uint64_t rr[4],
                                    const uint64_t ss[4]) {
   return guarded(ctx, [&](Ctx& c) {
-    B2Z_REQUIRE(pk && r && z && rr && ss, B2Z_EINVAL, "b2z_groth16_shard_begin: NULL argument");
+    B2Z_REQUIRE(pk && r && rr && ss, B2Z_EINVAL, "b2z_groth16_shard_begin: NULL argument");
     R1csImpl& R = r->impl;
     B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_shard_begin: key and matrices disagree");
-    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
-    B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
+    shard_assignment(c, R, z, "b2z_groth16_shard_begin");
+    B2Z_CUDA(cudaStreamWaitEvent(c.aux[0], R.ev_z, 0));
     prove_begin_on(c, pk, R.z.p, rr, ss);
   });
 }
 
-b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r, uint32_t which, uint64_t* d_out) {
+b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r, uint32_t which, const uint64_t* z, uint64_t* d_out) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(r && d_out && which < 3, B2Z_EINVAL, "b2z_r1cs_coset_evals: bad argument");
     R1csImpl& R = r->impl;
+    shard_assignment(c, R, z, "b2z_r1cs_coset_evals");
     cudaStream_t st = c.stream;
     B2Z_CUDA(cudaStreamWaitEvent(st, R.ev_z, 0));
     FrEl* out = reinterpret_cast<FrEl*>(d_out);

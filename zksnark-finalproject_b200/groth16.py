@@ -589,19 +589,23 @@ class Groth16:
 
     @staticmethod
     def shard_begin(ctx, pk, cm, full_assignment, r, s):
-        """b2z_groth16_shard_begin: upload z, start the z-only part of this shard (asynchronous)."""
+        """b2z_groth16_shard_begin: start the z-only part of this shard (asynchronous).  full_assignment:
+        the Montgomery limbs of z, or None when coset_evals already uploaded it for this proof."""
         cm.upload(ctx)
-        z = _fr_array(full_assignment)
+        z = _fr_array(full_assignment) if full_assignment is not None else None
         rs = codec.fr_to_mont_limbs([r, s])
         ctx.check(ctx._lib.b2z_groth16_shard_begin(ctx.handle, pk._handle, cm._handle, _ptr(z), _ptr(rs[0:1]),
                                                    _ptr(rs[1:2])))
         return z           # keep alive until shard_finish
 
     @staticmethod
-    def coset_evals(ctx, cm, which, device_ptr):
-        """b2z_r1cs_coset_evals: matrix `which` (0 A, 1 B, 2 C) against the z of shard_begin, transformed to the
-        coset, into a caller-owned device buffer (domain_size x 32 bytes)."""
-        ctx.check(ctx._lib.b2z_r1cs_coset_evals(ctx.handle, cm._handle, int(which), ctypes.c_void_p(int(device_ptr))))
+    def coset_evals(ctx, cm, which, device_ptr, full_assignment=None):
+        """b2z_r1cs_coset_evals: matrix `which` (0 A, 1 B, 2 C) against z, transformed to the coset, into a
+        caller-owned device buffer (domain_size x 32 bytes).  full_assignment as in shard_begin."""
+        cm.upload(ctx)
+        z = _fr_array(full_assignment) if full_assignment is not None else None
+        ctx.check(ctx._lib.b2z_r1cs_coset_evals(ctx.handle, cm._handle, int(which), _ptr(z),
+                                                ctypes.c_void_p(int(device_ptr))))
 
     @staticmethod
     def shard_finish(ctx, pk, d_a, d_b, d_c):
@@ -622,13 +626,17 @@ class Groth16:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         if buffers is None:
             buffers = [torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
-        keep = Groth16.shard_begin(ctx, pk, cm, full_assignment, r, s)
         owners = [j % world for j in range(3)]
+        z = _fr_array(full_assignment)
+        uploaded = False
+        # an owner transforms FIRST: once the accumulations fill its GPU nothing else gets scheduled
         for j in range(3):
             if owners[j] == rank:
-                Groth16.coset_evals(ctx, cm, j, buffers[j].data_ptr())
+                Groth16.coset_evals(ctx, cm, j, buffers[j].data_ptr(), None if uploaded else z)
+                uploaded = True
         works = [dist.broadcast(buffers[j], src=dist.get_global_rank(group, owners[j]) if group is not None else owners[j],
                                 group=group, async_op=True) for j in range(3)]
+        keep = Groth16.shard_begin(ctx, pk, cm, None if uploaded else z, r, s)
         for w in works:
             w.wait()
         torch.cuda.current_stream().synchronize()      # the library works on its own streams
