@@ -222,7 +222,8 @@ static_assert(kPartialBytes == B2Z_PARTIAL_BYTES, "header constant out of sync")
 // does the host epilogue.  The single-GPU prover runs them back to back; the sharded prover with a
 // distributed witness map (b2z_groth16_shard_*) lets the caller exchange the coset evaluations between
 // prove_begin and prove_quotient while the z-only accumulations are already running.
-void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
+void prove_accums(Ctx& c, PkImpl& pk);
+void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4], bool with_accums = true) {
   cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
   // host-side scalars: r, s, -(r s) as canonical integers
   const FrEl r_m = Fr::reduce(fr_load_host(r)), s_m = Fr::reduce(fr_load_host(s));
@@ -235,7 +236,6 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
   B2Z_CUDA(cudaMemcpyAsync(pk.tail.p, tail_h, sizeof(tail_h), cudaMemcpyHostToDevice, sA));
   fr_from_mont_device(&c, d_z + pk.lo, pk.zc.p, pk.ma, sA);     // this shard's slice of z as canonical integers
   B2Z_CUDA(cudaEventRecord(pk.ev_z, sA));
-  G1::Xyzz* g1o = pk.g1_out.p;   // 0 A, 3 L, 4 H, 5 B1
   const FrEl* z_l = pk.zc.p + (pk.l_lo - pk.lo);
   // ---- the four z-only sorts, concurrently
   msm_sort<G1>(&c, 1, pk.a_set, pk.zc.p, pk.ma, pk.tail.p + 0, sA);
@@ -249,6 +249,12 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
   B2Z_CUDA(cudaStreamWaitEvent(sL, pk.ev_z, 0));
   msm_sort<G1>(&c, 4, pk.l_set, z_l, pk.ml, pk.tail.p + 4, sL);
   B2Z_CUDA(cudaEventRecord(pk.ev_sorted[3], sL));
+  if (with_accums) prove_accums(c, pk);
+}
+
+void prove_accums(Ctx& c, PkImpl& pk) {
+  cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
+  G1::Xyzz* g1o = pk.g1_out.p;
   // ---- accumulations B -> A -> B1 -> L (-> H in prove_quotient), chained by events.
   // The G2 accumulation (255 registers: it fills every SM, nothing can be scheduled beside it) goes
   // first, right after the z-only sorts, so that its tail -- the longest -- hides under the G1
@@ -272,12 +278,15 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
 }
 
 // d_a, d_b, d_c: evaluations of the three QAP combinations on the coset g H (d_a is clobbered)
-void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c) {
+void prove_h_finish(Ctx& c, PkImpl& pk) {
+  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, c.stream, pk.ev_accum[2], nullptr, &pk.hp[4]);
+}
+void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, bool with_h_finish = true) {
   cudaStream_t st = c.stream;
   witness_map_quotient(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);    // whole domain, every shard
   fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
   msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);
-  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, st, pk.ev_accum[2], nullptr, &pk.hp[4]);
+  if (with_h_finish) prove_h_finish(c, pk);
 }
 
 void prove_end(Ctx& c, PkImpl& pk, uint8_t* partial_out) {
@@ -304,11 +313,14 @@ void prove_end(Ctx& c, PkImpl& pk, uint8_t* partial_out) {
 
 void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z, const uint64_t r[4],
                           const uint64_t s[4], uint8_t* partial_out) {
-  prove_begin(c, pk, d_z, r, s);
+  // issue order: everything light first (sorts, witness map, H sort), then the GPU-filling accumulations
+  prove_begin(c, pk, d_z, r, s, /*with_accums=*/false);
   witness_map_transform(&c, d_a, pk.log_n, c.stream);
   witness_map_transform(&c, d_b, pk.log_n, c.stream);
   witness_map_transform(&c, d_c, pk.log_n, c.stream);
-  prove_quotient(c, pk, d_a, d_b, d_c);
+  prove_quotient(c, pk, d_a, d_b, d_c, /*with_h_finish=*/false);
+  prove_accums(c, pk);
+  prove_h_finish(c, pk);
   prove_end(c, pk, partial_out);
 }
 
