@@ -157,6 +157,11 @@ B2Z_API b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
 #define B2Z_PARTIAL_BYTES 1344
 B2Z_API b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* desc, uint32_t rank, uint32_t world,
                                        b2z_pk** out);
+/* The same with an explicit slice: variables / h positions [total * from / den, total * to / den); the slice with
+ * from == 0 keeps the alpha/beta/delta terms.  Lets a caller give lighter shards to the GPUs that also transform one
+ * of the witness-map inputs (b2z_r1cs_coset_evals).  The slices of a proof must tile [0, den) in rank order.     */
+B2Z_API b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* desc, uint32_t from, uint32_t to, uint32_t den,
+                                       b2z_pk** out);
 B2Z_API b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk, const uint64_t* a_evals,
                                              const uint64_t* b_evals, const uint64_t* c_evals, const uint64_t* z,
                                              const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out);

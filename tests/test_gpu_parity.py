@@ -398,6 +398,26 @@ def test_prove_point_sharded_equals_whole_key(b2z, ctx, codec, circuits, world):
     pk.free()
 
 
+def test_prove_uneven_shards(b2z, ctx, codec, circuits):
+    """b2z_pk_upload_slice: shards of different sizes tile the key and combine to the whole-key proof."""
+    inst = circuits.matrix_circuit([[1, 2, 3], [4, 5, 6], [7, 8, 9]], [[2, 0, 1], [1, 1, 1], [3, 2, 1]])
+    rnd = random.Random(12)
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, inst.matrices, inst.num_constraints, inst.num_instance,
+                                                      inst.num_variables, *[rnd.randrange(1, R) for _ in range(5)])
+    want, (a, b, c) = _prove_gpu(b2z, ctx, codec, pk, inst, 5, 6)
+    z = codec.fr_to_mont_limbs(inst.z)
+    weights = [85, 100, 7, 100]
+    parts = []
+    for k in range(len(weights)):
+        shard = b2z.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                               pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                               pk.beta_g2, pk.delta_g2).upload(ctx, rank=k, world=len(weights), weights=weights)
+        parts.append(b2z.Groth16.create_proof_partial(ctx, shard, a, b, c, z, 5, 6))
+        shard.free()
+    assert b2z.Groth16.combine(parts) == want
+    pk.free()
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_prove_sharded_with_distributed_witness_map(b2z, ctx, codec, world):
     """b2z_groth16_shard_begin / b2z_r1cs_coset_evals / b2z_groth16_shard_finish: every shard gets the three

@@ -16,6 +16,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=8)
 ap.add_argument("--size", type=int, default=64)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--owner-weight", type=int, default=100,
+                help="points given to each of GPUs 0..2 per 100 given to each other GPU (with --distributed-wm)")
 ap.add_argument("--distributed-wm", action="store_true",
                 help="GPUs 0..2 transform a, b, c once and push the coset evaluations to their peers (copy engines)")
 args = ap.parse_args()
@@ -33,12 +35,15 @@ t_keygen = time.time() - t0
 pk.free()
 cm.free()
 shards, cms = [None] * G, [None] * G
+weights = None
+if args.distributed_wm and args.owner_weight != 100:
+    weights = [args.owner_weight if k < min(3, G) else 100 for k in range(G)]
 
 
 def setup(k):
     shards[k] = b.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
                              pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
-                             pk.beta_g2, pk.delta_g2).upload(ctxs[k], rank=k, world=G)
+                             pk.beta_g2, pk.delta_g2).upload(ctxs[k], rank=k, world=G, weights=weights)
     cms[k] = b.ConstraintMatrices(cm.num_instance_variables, cm.num_witness_variables, cm.num_constraints,
                                   cm.a, cm.b, cm.c).upload(ctxs[k])
 
@@ -128,7 +133,7 @@ ok = OG.verify(v, z_int[1:cm.num_instance_variables], O.proof_deserialize_compre
 line = {"mode": "point-sharded single proof, one process, one host thread per GPU"
                 + (", distributed witness map (peer copies)" if args.distributed_wm else ""), "n_gpus": G,
         "workload": "matrix %dx%d" % (n, n), "num_constraints": cm.num_constraints, "domain": cm.domain_size,
-        "ms_per_proof_wall": wall * 1e3, "proof_verifies": bool(ok), "keygen_s": t_keygen,
+        "ms_per_proof_wall": wall * 1e3, "shard_weights": weights, "proof_verifies": bool(ok), "keygen_s": t_keygen,
         "collective": "none (host sum of %d B per GPU)" % b._ffi.PARTIAL_BYTES,
         "inputs": "z in page-locked host memory (H2D to every GPU inside the timed region); rows evaluated on the GPU"}
 print(json.dumps(line))

@@ -45,6 +45,8 @@ SIGNATURES = {
     "b2z_spmv_fr": (ctypes.c_int32, [vp, ctypes.c_uint64, ctypes.c_uint64, vp, vp, vp, vp, vp]),
     "b2z_witness_map_from_matrices": (ctypes.c_int32, [vp, vp, vp, vp]),
     "b2z_groth16_prove_r1cs": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp]),
+    "b2z_pk_upload_slice": (ctypes.c_int32, [vp, ctypes.POINTER(PkDesc), ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, ctypes.POINTER(vp)]),
     "b2z_pk_upload_shard": (ctypes.c_int32, [vp, ctypes.POINTER(PkDesc), ctypes.c_uint32, ctypes.c_uint32,
                                              ctypes.POINTER(vp)]),
     "b2z_groth16_prove_partial": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -405,11 +405,12 @@ b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t
   return guarded(ctx, [&](Ctx& c) { fixed_base_entry<G2>(c, scalars, n, out_points, out_inf); });
 }
 
-b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank, uint32_t world, b2z_pk** out) {
+b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from, uint32_t to, uint32_t den,
+                               b2z_pk** out) {
   if (out) *out = nullptr;
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(d != nullptr && out != nullptr, B2Z_EINVAL, "b2z_pk_upload: NULL argument");
-    B2Z_REQUIRE(world >= 1 && rank < world, B2Z_EINVAL, "b2z_pk_upload_shard: need rank < world");
+    B2Z_REQUIRE(den >= 1 && from <= to && to <= den, B2Z_EINVAL, "b2z_pk_upload_slice: need from <= to <= den");
     B2Z_REQUIRE(d->log_domain <= 32, B2Z_ESIZE, "b2z_pk_upload: domain larger than 2^32");
     B2Z_REQUIRE(d->log_domain <= 26, B2Z_ENOMEM, "b2z_pk_upload: domain does not fit this build's single-GPU plan");
     B2Z_REQUIRE(d->num_instance >= 1 && d->num_variables >= d->num_instance, B2Z_EINVAL,
@@ -424,18 +425,18 @@ b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank
     P.log_n = d->log_domain;
     P.m = m;
     P.l = l;
-    // contiguous shards: variables [m rank / world, m (rank+1) / world), same fraction of the h positions
-    const uint64_t lo = m * rank / world, hi = m * (rank + 1) / world;
+    // contiguous shards: variables [m from / den, m to / den), same fraction of the h positions
+    const uint64_t lo = m * from / den, hi = m * to / den;
     const uint64_t l_lo = lo > l ? lo : l, l_hi = hi > l ? hi : l;      // witness variables in the slice
-    const uint64_t h_lo = n * rank / world, h_hi = n * (rank + 1) / world;
+    const uint64_t h_lo = n * from / den, h_hi = n * to / den;
     P.lo = (uint32_t)lo; P.ma = (uint32_t)(hi - lo);
     P.l_lo = (uint32_t)l_lo; P.ml = (uint32_t)(l_hi - l_lo);
     P.h_lo = (uint32_t)h_lo; P.hn = (uint32_t)(h_hi - h_lo);
-    P.with_vk = rank == 0 ? 1u : 0u;
+    P.with_vk = from == 0 ? 1u : 0u;
     cudaStream_t st = c.stream;
     size_t free_b = 0, total_b = 0;
     B2Z_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    const bool pre = pk_precompute_bytes(d) / world < free_b / 2;
+    const bool pre = pk_precompute_bytes(d) / den * (to - from) < free_b / 2;
     auto sub_inf = [](const uint8_t* inf, uint64_t from, uint64_t count, std::vector<uint8_t>& tmp) -> const uint8_t* {
       if (inf == nullptr) return nullptr;
       tmp.assign((count + 7) / 8 + 1, 0);
@@ -521,8 +522,16 @@ b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank
   });
 }
 
+b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank, uint32_t world, b2z_pk** out) {
+  if (world < 1 || rank >= world) {
+    if (out) *out = nullptr;
+    return guarded(ctx, [&](Ctx&) { B2Z_REQUIRE(false, B2Z_EINVAL, "b2z_pk_upload_shard: need rank < world"); });
+  }
+  return b2z_pk_upload_slice(ctx, d, rank, rank + 1, world, out);
+}
+
 b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {
-  return b2z_pk_upload_shard(ctx, d, 0, 1, out);
+  return b2z_pk_upload_slice(ctx, d, 0, 1, 1, out);
 }
 
 b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk_c, const uint64_t* a_evals, const uint64_t* b_evals,

@@ -349,9 +349,10 @@ class ProvingKey:
         self._ctx = None
         self._handle = None
 
-    def upload(self, ctx, rank=0, world=1):
+    def upload(self, ctx, rank=0, world=1, weights=None):
         """b2z_pk_upload / b2z_pk_upload_shard: copies the key (or this rank's point shard of
-        it) to the device, once per circuit."""
+        it) to the device, once per circuit.  weights (one positive integer per rank): uneven
+        shards through b2z_pk_upload_slice -- rank k gets weights[k] / sum(weights) of the points."""
         if self._handle is not None:
             return self
         keep = []
@@ -378,7 +379,14 @@ class ProvingKey:
         d.alpha_g1, d.beta_g1, d.delta_g1 = p(self.alpha_g1), p(self.beta_g1), p(self.delta_g1)
         d.beta_g2, d.delta_g2 = p(self.beta_g2), p(self.delta_g2)
         h = ctypes.c_void_p()
-        ctx.check(ctx._lib.b2z_pk_upload_shard(ctx.handle, ctypes.byref(d), int(rank), int(world), ctypes.byref(h)))
+        if weights is not None:
+            if len(weights) != world or min(weights) <= 0:
+                raise ValueError("weights: one positive integer per rank")
+            lo, den = sum(weights[:rank]), sum(weights)
+            ctx.check(ctx._lib.b2z_pk_upload_slice(ctx.handle, ctypes.byref(d), int(lo), int(lo + weights[rank]),
+                                                   int(den), ctypes.byref(h)))
+        else:
+            ctx.check(ctx._lib.b2z_pk_upload_shard(ctx.handle, ctypes.byref(d), int(rank), int(world), ctypes.byref(h)))
         self._ctx, self._handle = ctx, h
         self.shard = (int(rank), int(world))
         return self
