@@ -250,6 +250,11 @@ B2Z_API int b2z_host_point_sum(int group /*1|2*/, const uint32_t* points, const 
 /* signed digits of a canonical scalar as the MSM kernels see them; returns the window count */
 B2Z_API uint32_t b2z_host_msm_digits(const uint32_t scalar[8], uint32_t c, int32_t* digits /* >= 64 */);
 B2Z_API uint32_t b2z_host_msm_window_bits(uint64_t n, int precomputed);
+/* the host-side last step of an MSM (csrc/host_fq.hpp, what the prover's epilogue runs): planes[0] +
+ * 2^chunk_log * sum_{k>=1} 2^(k-1) planes[k] for nplanes XYZZ points in the device layout (48 / 96 u32 each),
+ * serialised compressed (48 / 96 bytes) into out                                                                */
+B2Z_API int b2z_host_planes_horner(int group /*1|2*/, const uint32_t* planes_xyzz, uint32_t nplanes, uint32_t chunk_log,
+                                   uint8_t* out);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,47 @@ def test_device_point_arithmetic_on_host(b2z, group):
     assert rc == 1                                                          # P + (-P) is the identity
 
 
+@pytest.mark.parametrize("group", [1, 2])
+def test_host_epilogue_planes_horner(b2z, group):
+    """host_fq.hpp (the prover's host epilogue): the serial last step of every MSM -- planes[0] +
+    2^chunk_log * sum 2^(k-1) planes[k] over XYZZ points -- and the zcash serialization, vs the oracle."""
+    L = b2z._ffi.lib()
+    curve = O.G1 if group == 1 else O.G2
+    rnd = random.Random(40 + group)
+    q = O.Q_MOD
+    for nplanes, chunk_log in ((0, 3), (1, 3), (2, 3), (13, 3), (7, 2)):
+        pts = [curve.mul(curve.gen, rnd.randrange(1, 1 << 30)) for _ in range(nplanes)]
+        if nplanes > 4:
+            pts[2] = None                      # an empty plane
+            pts[4] = pts[3]                    # forces a doubling inside an addition
+        words = []
+        for p in pts:
+            if p is None:
+                coords = [0] * (4 * group)
+            elif group == 1:
+                t = rnd.randrange(1, q)        # a non-trivial XYZZ representative: (x t^2, y t^3, t^2, t^3)
+                coords = [p[0] * t * t % q, p[1] * pow(t, 3, q) % q, t * t % q, pow(t, 3, q)]
+            else:
+                t = (rnd.randrange(1, q), rnd.randrange(q))
+                F = O.Fq2Ops
+                t2 = F.sqr(t); t3 = F.mul(t2, t)
+                coords = [v for pair in (F.mul(p[0], t2), F.mul(p[1], t3), t2, t3) for v in pair]
+            for v in coords:
+                words.append(_arr32(O.fq_to_mont(v), 12))
+        planes = np.concatenate(words) if words else np.zeros(1, dtype=np.uint32)
+        out = np.zeros(48 * group, dtype=np.uint8)
+        assert L.b2z_host_planes_horner(group, planes.ctypes.data, nplanes, chunk_log, out.ctypes.data) == 0
+        want = pts[0] if nplanes else None
+        if nplanes > 1:
+            h = None
+            for k in range(nplanes - 1, 0, -1):
+                h = curve.add(curve.add(h, h), pts[k])
+            for _ in range(chunk_log):
+                h = curve.add(h, h)
+            want = curve.add(want, h)
+        assert out.tobytes() == (O.g1_compress if group == 1 else O.g2_compress)(want), (nplanes, chunk_log)
+
+
 @pytest.mark.parametrize("c", [4, 5, 8, 11, 13, 15, 16, 17, 20])
 def test_msm_digit_recoding(b2z, c):
     L = b2z._ffi.lib()

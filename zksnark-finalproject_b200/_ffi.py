@@ -69,6 +69,7 @@ SIGNATURES = {
     "b2z_host_point_sum": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_uint32, vp]),
     "b2z_host_msm_digits": (ctypes.c_uint32, [vp, ctypes.c_uint32, vp]),
     "b2z_host_msm_window_bits": (ctypes.c_uint32, [ctypes.c_uint64, ctypes.c_int]),
+    "b2z_host_planes_horner": (ctypes.c_int, [ctypes.c_int, vp, ctypes.c_uint32, ctypes.c_uint32, vp]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@
 // by the proving path.
 #include <cstring>
 
+#include "host_fq.hpp"
 #include "msm.hpp"
 
 using namespace b2z;
@@ -74,6 +75,13 @@ uint32_t b2z_host_msm_digits(const uint32_t scalar[8], uint32_t c, int32_t* digi
   for (uint32_t w = 0; w < cfg.windows; w++) digits[w] = 0;
   for_each_digit(k, cfg, [&](uint32_t w, uint32_t v, bool neg) { digits[w] = neg ? -(int32_t)v : (int32_t)v; });
   return cfg.windows;
+}
+
+int b2z_host_planes_horner(int group, const uint32_t* planes_xyzz, uint32_t nplanes, uint32_t chunk_log, uint8_t* out) {
+  if (out == nullptr || (nplanes && planes_xyzz == nullptr)) return -1;
+  if (group == 1) host::g1_serialize(out, host::g1_planes_horner(planes_xyzz, nplanes, chunk_log));
+  else host::g2_serialize(out, host::g2_planes_horner(planes_xyzz, nplanes, chunk_log));
+  return 0;
 }
 
 uint32_t b2z_host_msm_window_bits(uint64_t n, int precomputed) { return msm_pick_c(n, precomputed != 0); }
