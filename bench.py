@@ -384,9 +384,9 @@ def main():
         "bound": "hbm", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None, "peak": hbm_peak,
         "unit": "GB/s", "frac": (acc_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak) if acc_ms else None,
         # dram__bytes_read+write of one G1 accumulation launch from the committed ncu --set full capture
-        # (profiles/r01_ncu/prof_accum_g1.raw.csv: 855.1 MB for the 5.13 M-addition C_z launch = 167 B per
-        # mixed addition), scaled to this run's average launch
-        "traffic": acc_adds * 167.0,
+        # (profiles/r01_ncu/prof_accum_g1.raw.csv: 245.8 MB read + 8.6 MB written by the 1.63 M-addition launch of
+        # the A query = 156 B per mixed addition, 1.56x the algorithmic 100 B), scaled to this run's average launch
+        "traffic": acc_adds * 156.0,
         "peak_source": hbm_src,
         "note": "this kernel is integer-pipe bound, not HBM bound (SURVEY.md App. C): see int_pipe",
         "int_pipe": {

@@ -7,7 +7,7 @@ CMD="python bench.py --steps 2 --warmup 3 --cpu-steps 0"
 $CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain.err; exit 1; }
 SKIP=$(grep -o 'before the timed region: [0-9]*' gpurun_out/ncu_plain.err | grep -o '[0-9]*$')
 echo "library kernels before the timed region: $SKIP"
-KREGEX='regex:msm_|ntt_|wm_|scalar_prep|fr_from_mont|canonicalize|scan_|bitrev|pack_flags|fb_|batch_norm|twiddle|pow_table'
+KREGEX='regex:msm_|ntt_|wm_|scalar_prep|fr_from_mont|canonicalize|scan_|bitrev|pack_flags|fb_|batch_norm|twiddle|pow_table|r1cs_|spmv_'
 # the timed region of this command is 2 steps of ~83 launches; list one of them (+ a few)
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s $SKIP -c 100 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
