@@ -264,22 +264,29 @@ void prove_accums(Ctx& c, PkImpl& pk) {
   // by the HOST (prove_end) while the GPU is still busy with L and H.  (With the scalar multiplications
   // on the GPU -- 1.5 ms each even with lane-cooperative arithmetic -- every order tried put one of them
   // on the critical path: 7.65-8.3 ms per C2 proof.)
-  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
-  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
-  B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
+  // Chaining only pays when an accumulation fills the GPU: below ~64 k point references it is a few blocks
+  // and the chain would just add its kernels' latencies (Fibonacci: 5 variables) -- those run concurrently.
+  auto big = [](uint64_t n, uint32_t windows) { return n * windows >= (1u << 16); };
+  const bool chain = big(pk.g2.n, pk.g2.windows) || big(pk.a_set.n, pk.a_set.windows);
+  if (chain) {
+    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
+    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
+    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
+  }
   msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3], &pk.hp[1]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
-  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, pk.ev_accum[3], pk.ev_accum[0], &pk.hp[0]);
+  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, chain ? pk.ev_accum[3] : nullptr, pk.ev_accum[0], &pk.hp[0]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], sA));
-  msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, pk.ev_accum[0], pk.ev_accum[1], &pk.hp[2]);
+  msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, chain ? pk.ev_accum[0] : nullptr, pk.ev_accum[1], &pk.hp[2]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], sB1));
-  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, pk.ev_accum[1], pk.ev_accum[2], &pk.hp[3]);
+  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, chain ? pk.ev_accum[1] : nullptr, pk.ev_accum[2], &pk.hp[3]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], sL));
 }
 
 // d_a, d_b, d_c: evaluations of the three QAP combinations on the coset g H (d_a is clobbered)
 void prove_h_finish(Ctx& c, PkImpl& pk) {
-  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, c.stream, pk.ev_accum[2], nullptr, &pk.hp[4]);
+  const bool chain = (uint64_t)pk.h.n * pk.h.windows >= (1u << 16);
+  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, c.stream, chain ? pk.ev_accum[2] : nullptr, nullptr, &pk.hp[4]);
 }
 void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, bool with_h_finish = true) {
   cudaStream_t st = c.stream;
