@@ -562,3 +562,42 @@ def test_error_codes(b2z, ctx):
     # the context is still usable after an error
     dom = b2z.Radix2EvaluationDomain(ctx, 2)
     assert b2z.codec.fr_from_mont_limbs(dom.fft(b2z.codec.fr_to_mont_limbs([1, 2]))) == [3, R - 1]
+
+
+def test_error_codes_of_the_shard_entry_points(b2z, ctx, codec):
+    """Misuse of the sharded entry points is reported as a status, never a crash, and leaves the context usable."""
+    import ctypes
+    import importlib
+    import torch
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    L, F = b2z._ffi.lib(), b2z._ffi
+    cm, z_int = fast.matrix_circuit_fast([[1, 2], [3, 4]], [[4, 3], [2, 1]])
+    rnd = random.Random(8)
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                      cm.num_variables, *[rnd.randrange(1, R) for _ in range(5)])
+    z = codec.fr_to_mont_limbs(z_int)
+    want = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, 3, 4)
+    fresh = b2z.ConstraintMatrices(cm.num_instance_variables, cm.num_witness_variables, cm.num_constraints,
+                                   cm.a, cm.b, cm.c).upload(ctx)
+    rs = codec.fr_to_mont_limbs([3, 4])
+    buf = torch.empty((pk.domain_size, 4), dtype=torch.int64, device="cuda")
+    ptr = ctypes.c_void_p(buf.data_ptr())
+    # no assignment was ever uploaded for these matrices
+    assert L.b2z_groth16_shard_begin(ctx.handle, pk._handle, fresh._handle, None, rs[0:1].ctypes.data,
+                                     rs[1:2].ctypes.data) == F.B2Z_EINVAL
+    assert b"no assignment" in L.b2z_last_error(ctx.handle)
+    assert L.b2z_r1cs_coset_evals(ctx.handle, fresh._handle, 1, None, ptr) == F.B2Z_EINVAL
+    assert L.b2z_r1cs_coset_evals(ctx.handle, fresh._handle, 3, z.ctypes.data, ptr) == F.B2Z_EINVAL
+    assert L.b2z_groth16_shard_finish(ctx.handle, pk._handle, ptr, None, ptr, None) == F.B2Z_EINVAL
+    # slices: from <= to <= den
+    with pytest.raises(b2z._ffi.B2zError):
+        b2z.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query, pk.b_g2_query,
+                       pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1, pk.beta_g2,
+                       pk.delta_g2).upload(ctx, rank=2, world=2)
+    h = ctypes.c_void_p()
+    assert L.b2z_host_register(ctx.handle, None, 16) == F.B2Z_EINVAL
+    # still proving correctly afterwards
+    assert b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, 3, 4) == want
+    fresh.free()
+    cm.free()
+    pk.free()
