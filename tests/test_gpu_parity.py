@@ -339,6 +339,32 @@ def test_prove_matrix_16x16_full_size(b2z, ctx, codec, cpu_oracle, circuits):
     _setup_prove_verify(b2z, ctx, codec, cpu_oracle, inst, 4)
 
 
+def test_prove_matrix_20x20_reference_fixture(b2z, ctx, codec, cpu_oracle):
+    """The reference's own large test case (matrix_proof_of_work/constraints.rs:280-285): 20x20 matrices with
+    A[i][j] = i, B[i][j] = j -- 175 003 constraints, domain 2^18; rows evaluated on the GPU, proof bytes equal
+    the C++ oracle's on the same key and pass the pairing check."""
+    import importlib
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    n = 20
+    cm, z_int = fast.matrix_circuit_fast([[i] * n for i in range(n)], [[j for j in range(n)] for _ in range(n)])
+    assert cm.num_constraints == 3 * ((n * n + 1) // 2) * 265 + 2 * n ** 3 + 3 and cm.domain_size == 1 << 18
+    rnd = random.Random(2020)
+    pk, vk = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                       cm.num_variables, *[rnd.randrange(1, R) for _ in range(5)])
+    z = codec.fr_to_mont_limbs(z_int)
+    r, s = rnd.randrange(R), rnd.randrange(R)
+    got = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r, s)
+    a, b, c = b2z.LibsnarkReduction.constraint_evaluations_device(ctx, cm, z)
+    cpk = cpu_oracle.CpuProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                                   pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                                   pk.beta_g2, pk.delta_g2)
+    rs = codec.fr_to_mont_limbs([r, s])
+    assert got == cpk.prove(a, b, c, z, rs[0], rs[1])
+    assert OG.verify(_vk_as_oracle(codec, vk), z_int[1:cm.num_instance_variables], O.proof_deserialize_compressed(got))
+    cm.free()
+    pk.free()
+
+
 # ------------------------------------------------------------------------------- constraint matrices on the device
 def test_r1cs_rows_witness_map_and_prove_on_device(b2z, ctx, codec, circuits):
     """Row f1: the evaluate_constraint loop, witness_map_from_matrices and the whole prove with
