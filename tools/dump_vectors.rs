@@ -33,7 +33,11 @@ use ark_relations::r1cs::{ConstraintSynthesizer, ConstraintSystem, OptimizationG
 use ark_serialize::CanonicalSerialize;
 use ark_snark::SNARK;
 use ark_std::rand::{rngs::StdRng, SeedableRng};
+use ark_r1cs_std::alloc::AllocVar;
 use prime_snarks::arkworks::constraints::fibbonaci::FibonacciCircuit;
+use prime_snarks::arkworks::matrix_proof_of_work::alloc::FpVar2DVec;
+use prime_snarks::arkworks::matrix_proof_of_work::constraints::{matrix_mul, MatrixCircuit};
+use prime_snarks::arkworks::matrix_proof_of_work::hasher::hasher;
 use std::fmt::Write as _;
 
 fn fr(x: &Fr) -> String { format!("\"{}\"", x.into_bigint()) }
@@ -121,9 +125,20 @@ fn main() {
     write_case(&dir, "fibonacci_0_1_10",
                FibonacciCircuit::<Fr> { a: Some(Fr::from(0u64)), b: Some(Fr::from(1u64)), num_of_steps: 10, result: Some(Fr::from(55u64)) },
                0xB2000004);
-    // The matrix circuit (matrix_proof_of_work/constraints.rs:234-271) and the prime circuit
-    // (prime_snark/prime_circut.rs:361) are dumped the same way: build the circuit value exactly as the
-    // reference's own test does (the hashes come from `hasher(...)` on the allocated matrices) and call
-    //     write_case(&dir, "matrix_2x2", circuit, 0xB2000004);
-    // Their matrices travel inside the dump, so the checker needs no knowledge of the Poseidon / SHA-256 gadgets.
+    // matrix_proof_of_work/constraints.rs:231-271: [[1,2],[3,4]] * [[4,3],[2,1]], hashes computed the way the
+    // reference's own test computes them (a scratch constraint system just to obtain the three digests)
+    for (case, a, b) in [
+        ("matrix_2x2", vec![vec![1u64, 2], vec![3, 4]], vec![vec![4u64, 3], vec![2, 1]]),
+        ("matrix_4x4_ones", vec![vec![1u64; 4]; 4], vec![vec![1u64; 4]; 4]),
+    ] {
+        let scratch = ConstraintSystem::<Fr>::new_ref();
+        let av = FpVar2DVec::new_witness(scratch.clone(), || Ok(a.clone())).unwrap();
+        let bv = FpVar2DVec::new_witness(scratch.clone(), || Ok(b.clone())).unwrap();
+        let cv = matrix_mul(scratch.clone(), av.clone(), bv.clone());
+        let (ha, hb, hc) = (hasher(&av).unwrap()[0], hasher(&bv).unwrap()[0], hasher(&cv).unwrap()[0]);
+        write_case(&dir, case, MatrixCircuit::<Fr>::new(a, b, ha, hb, hc), 0xB2000004);
+    }
+    // The prime circuit (prime_snark/prime_circut.rs:361, x = 5) is dumped the same way: build the circuit value
+    // exactly as its own test does and call write_case(&dir, "prime_5", circuit, 0xB2000004).  The matrices travel
+    // inside the dump, so the checker needs no knowledge of the Poseidon / SHA-256 gadgets.
 }
