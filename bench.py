@@ -1,27 +1,31 @@
 #!/usr/bin/env python3
 """Benchmark of the Groth16 prove path (BASELINE.json metric: Groth16 prove ms & proofs/s).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c5]
 
-One "step" = one full proof of the workload circuit: witness map (7 NTTs) + 4 G1 MSMs +
-1 G2 MSM + combine + serialization, from the constraint-row evaluations / assignment to
-the 192 proof bytes.  Synthesis, key generation and key upload are outside the timed
-region.
+One "step" = one full proof of the workload circuit: constraint-row evaluation, witness map
+(7 NTTs), 4 G1 MSMs + 1 G2 MSM, combine, serialization -- from the assignment z to the 192 proof
+bytes.  Synthesis, key generation and key upload are outside the timed region.
+Default workload: BASELINE configs[4], the 64x64 matrix-multiplication circuit (2 152 451
+constraints, domain 2^22) -- the north-star configuration; it fits one GPU (about 25 GB of key).
 
-  value      proofs/s with inputs resident in HBM (b2z_groth16_prove_device)
-  e2e        proofs/s through b2z_groth16_prove with pinned HOST buffers: H2D of a, b, c, z
-             and D2H of the proof inside the timed region
-  roofline   the dominant kernel (G1 bucket accumulation), timed live with CUDA events
-             on its own stream by the library's phase timers
-  cpu_baseline  oracle/cpu (arkworks-algorithm restatement) on the host cores, N=1 only
+  N = 1   value   proofs/s, assignment already resident in HBM (b2z_groth16_prove_r1cs, device z)
+          e2e     the same call with z in pinned HOST memory: H2D of z and D2H of the result inside
+  N > 1   ONE proof computed by all N GPUs (point-sharded MSMs) -> "scaling": "strong";
+          value / e2e as above (z resident on every GPU / z in pinned host memory on every rank).
+          "replicas" (extra key): one independent proof per GPU, no data-path collective.
+  roofline      the dominant kernel (G1 bucket accumulation) timed live with CUDA events on its own
+                stream by the library's phase timers, against the measured 32-bit IMAD issue rate
+  cpu_baseline  oracle/cpu (arkworks-algorithm C++ restatement) on the host cores, N = 1 only
+  extra.c2      BASELINE configs[1] (16x16, domain 2^17), measured the same way, for continuity
 
-N > 1: one process per GPU (torchrun), every rank proves its own proof of the same circuit
-(independent proofs batch one per GPU, no data-path collective) -> "scaling": "weak".
-`--impl reference` times the CPU restatement (the reference itself is Rust on un-vendored
-crates and cannot be built here); rank 0 only.
+`--impl reference` times the CPU restatement end to end (key generation, row evaluation and proof
+all in oracle/cpu: the GPU library is never loaded); the Rust reference itself cannot be built
+here (no cargo, un-vendored crates).  Rank 0 only.
 """
 import argparse
 import ctypes
+import hashlib
 import importlib
 import json
 import os
@@ -39,15 +43,15 @@ R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 SEED = 0xB2000004
 
 WORKLOADS = {
-    # name: (description, builder)
     "c1": "Fibonacci n=1000 (BASELINE configs[0]): domain 2^10, 5 variables",
     "c2": "matrix-multiplication 16x16 with Poseidon-shaped hashes (BASELINE configs[1]): "
           "109955 constraints, domain 2^17",
     "m8": "matrix-multiplication 8x8 (development size): domain 2^15",
     "c3": "prime-SNARK shape (BASELINE configs[2]): 7 SHA-256-sized Boolean blocks + 3 Fermat modpows, NUM_BITS=20",
-    "c5": "matrix-multiplication 64x64 with Poseidon-shaped hashes (BASELINE configs[4] shape): "
+    "c5": "matrix-multiplication 64x64 with Poseidon-shaped hashes (BASELINE configs[4]): "
           "2152451 constraints, domain 2^22",
 }
+DTYPE = "u32 limbs (Fr 255-bit / Fq 381-bit integers)"
 
 
 class Instance:
@@ -60,7 +64,7 @@ class Instance:
 
 
 def build_instance(name):
-    pkg = importlib.import_module(PKG)
+    pkg = importlib.import_module(PKG)          # import only: the CUDA library is loaded by Context()
     if name == "c1":
         inst = importlib.import_module(PKG + ".circuits").fibonacci_circuit(0, 1, 1000)
         cm = pkg.ConstraintMatrices.from_rows(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c)
@@ -73,6 +77,15 @@ def build_instance(name):
     ones = [[1] * n for _ in range(n)]                 # bench/matrix.py:10-11 posts all-ones matrices
     cm, z = importlib.import_module(PKG + ".circuits_fast").matrix_circuit_fast(ones, ones)
     return Instance(cm, z)
+
+
+def config_of(name, inst, world):
+    """The SAME dict for both arms (the driver compares them)."""
+    return {"workload": WORKLOADS[name], "num_constraints": inst.num_constraints, "domain": inst.domain_size,
+            "num_variables": inst.num_variables,
+            "parallelism": "1 GPU" if world == 1 else "one proof point-sharded over %d GPUs" % world,
+            "cache_policy": "inputs larger than L2: every proof streams the whole proving key (>> 126 MB L2) "
+                            "plus its assignment; no explicit flush"}
 
 
 class ClockSampler:
@@ -125,67 +138,54 @@ def toxic_waste():
     return [rnd.randrange(1, R_MOD) for _ in range(5)]
 
 
-def cpu_prove_setup(pkg, inst, pk):
-    from oracle import cpu_oracle
-    cpk = cpu_oracle.CpuProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
-                                   pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
-                                   pk.beta_g2, pk.delta_g2)
-    return cpu_oracle, cpk
+def proof_scalars(rank=0):
+    rnd = random.Random(SEED ^ 1 ^ (rank << 8))
+    return rnd.randrange(R_MOD), rnd.randrange(R_MOD)
 
 
+# ----------------------------------------------------------------------------------------------------
+# reference arm: CPU only
+# ----------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """CPU arm: oracle/cpu (arkworks-algorithm restatement) with all host threads."""
+    """oracle/cpu (arkworks-algorithm restatement) with all host threads; nothing of the product's CUDA
+    library is loaded: key generation (ark_cpu_groth16_setup), row evaluation and the proof are all CPU."""
     if rank != 0:
         return
+    from oracle import cpu_oracle
     pkg = importlib.import_module(PKG)
     codec = pkg.codec
+    t0 = time.perf_counter()
     inst = build_instance(args.workload)
-    # the key must be valid for the circuit; group elements are made on the GPU when there is one,
-    # else (no GPU on this host) by the Python oracle -- either way outside the timed region
-    try:
-        ctx = pkg.Context(0)
-        pk, _ = pkg.Groth16.generate_parameters_with_qap(ctx, inst.cm, inst.num_constraints, inst.num_instance,
-                                                         inst.num_variables, *toxic_waste())
-        a, b, c = pkg.LibsnarkReduction.constraint_evaluations_device(ctx, inst.cm, codec.fr_to_mont_limbs(inst.z))
-        ctx.close()
-    except Exception:
-        from oracle import groth16 as OG
-        ra, rb, rc = inst.cm.rows()
-        a, b, c = pkg.LibsnarkReduction.constraint_evaluations((ra, rb, rc), inst.num_instance, inst.num_constraints,
-                                                               inst.z)
-        opk = OG.setup(OG.R1CS(inst.num_instance, inst.num_variables - inst.num_instance, ra, rb, rc),
-                       toxic=toxic_waste())
-        q1, q2 = codec.g1_to_limbs, codec.g2_to_limbs
-        pk = pkg.ProvingKey(opk.num_variables, opk.num_instance, opk.domain_size, q1(opk.a_query), q1(opk.b_g1_query),
-                            q2(opk.b_g2_query), q1(opk.h_query), q1(opk.l_query), q1([opk.alpha_g1])[0][0],
-                            q1([opk.beta_g1])[0][0], q1([opk.delta_g1])[0][0], q2([opk.beta_g2])[0][0],
-                            q2([opk.delta_g2])[0][0])
-    cpu_oracle, cpk = cpu_prove_setup(pkg, inst, pk)
+    cm = inst.cm
     cores = cpu_oracle.hardware_threads()
     cpu_oracle.set_threads(cores)
+    key = cpu_oracle.groth16_setup(cm.a, cm.b, cm.c, cm.num_constraints, cm.num_instance_variables, cm.num_variables,
+                                   toxic_waste())
+    cpk = cpu_oracle.proving_key_of(key)
     z = codec.fr_to_mont_limbs(inst.z)
-    rnd = random.Random(SEED ^ 1)
-    rs = codec.fr_to_mont_limbs([rnd.randrange(R_MOD), rnd.randrange(R_MOD)])
+    a, b, c = cpu_oracle.constraint_evals(cm.a, cm.b, cm.c, cm.num_constraints, cm.num_instance_variables, z)
+    rs = codec.fr_to_mont_limbs(list(proof_scalars(0)))
+    setup_s = time.perf_counter() - t0
+    print("[bench reference] circuit + CPU key generation: %.1f s" % setup_s, file=sys.stderr, flush=True)
+    proof = None
     for _ in range(args.warmup):
-        cpk.prove(a, b, c, z, rs[0], rs[1])
+        proof = cpk.prove(a, b, c, z, rs[0], rs[1])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpk.prove(a, b, c, z, rs[0], rs[1])
+        proof = cpk.prove(a, b, c, z, rs[0], rs[1])
     dt = (time.perf_counter() - t0) / args.steps
     val = 1.0 / dt
-    line = {
+    emit({
         "impl": "reference", "metric": "groth16_proofs_per_sec", "value": val, "unit": "proofs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Fr 255-bit / Fq 381-bit integers)",
-        "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "num_constraints": inst.num_constraints,
-                   "domain": inst.domain_size, "num_variables": inst.num_variables},
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u64 limbs (Fr 255-bit / Fq 381-bit integers)",
+        "data": "synthetic", "config": config_of(args.workload, inst, world),
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": cores, "kind": "port",
-                         "sample": "%d full proofs of the same workload; arkworks-algorithm C++ restatement "
-                                   "(the Rust reference cannot be built here)" % args.steps},
+                         "sample": "%d full proofs of the same workload; arkworks-algorithm C++ restatement incl. its own "
+                                   "CPU key generation (the Rust reference cannot be built here)" % args.steps},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    emit(line)
+        "setup_s": setup_s, "proof_sha": hashlib.sha256(proof).hexdigest()[:16],
+    })
 
 
 _REAL_STDOUT = None
@@ -202,6 +202,293 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args, rank, local_rank, world):
+        import numpy as np
+        import torch
+        self.np, self.torch = np, torch
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        self.pkg = importlib.import_module(PKG)
+        self.codec = self.pkg.codec
+        self.ctx = self.pkg.Context(local_rank)
+        self.L = self.ctx._lib
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+
+    # ---- timing helpers
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events (every step ends with its
+        result in host memory, so the events bracket all the work); max over ranks."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        wall = time.perf_counter() - w0
+        dev_s = e0.elapsed_time(e1) * 1e-3
+        t = torch.tensor([max(dev_s, 0.0), wall], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    # ---- one workload
+    def measure(self, name, steps, warmup, main):
+        """Returns the result dict of one workload (rank 0; None elsewhere for the JSON part)."""
+        np, torch, pkg, codec, ctx, L = self.np, self.torch, self.pkg, self.codec, self.ctx, self.L
+        rank, world = self.rank, self.world
+        log = lambda msg: print("[bench r%d %s] %s" % (rank, name, msg), file=sys.stderr, flush=True)
+        t0 = time.perf_counter()
+        inst = build_instance(name)
+        cm = inst.cm
+        pk, vk = pkg.Groth16.generate_parameters_with_qap(ctx, cm, inst.num_constraints, inst.num_instance,
+                                                          inst.num_variables, *toxic_waste())
+        log("circuit + GPU key generation %.1f s" % (time.perf_counter() - t0))
+        n, m = inst.domain_size, inst.num_variables
+        p = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+        hp = lambda t: ctypes.c_void_p(t.data_ptr())
+        z = codec.fr_to_mont_limbs(inst.z)
+        z_host = torch.from_numpy(z.view(np.int64).copy()).pin_memory()      # pinned host copy (e2e arm)
+        z_dev = z_host.cuda()                                                # resident copy (value arm)
+        cm.upload(ctx)
+        proof = np.zeros(192, dtype=np.uint8)
+        res = {}
+
+        if world == 1:
+            pk.upload(ctx)
+            r, s = proof_scalars(0)
+            rs = codec.fr_to_mont_limbs([r, s])
+
+            def step(zt):
+                ctx.check(L.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, cm._handle, hp(zt), p(rs[0:1]), p(rs[1:2]),
+                                                   p(proof)))
+            step_value = lambda: step(z_dev)
+            step_e2e = lambda: step(z_host)
+            collective = None
+        else:
+            # ---- ONE proof by all ranks: every rank holds 1/N of every base set; the three input transforms
+            # of the witness map are done once in the group (rank j % N owns matrix j) and broadcast
+            dist = self.dist
+            spk = pk.upload(ctx, rank=rank, world=world)
+            r, s = proof_scalars(0)                                            # the same r, s on every rank
+            rs = codec.fr_to_mont_limbs([r, s])
+            bufs = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+            owners = [j % world for j in range(3)]
+            part = np.zeros(pkg._ffi.PARTIAL_BYTES, dtype=np.uint8)
+            gathered = [torch.empty(pkg._ffi.PARTIAL_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            out = {}
+
+            def step(zt):
+                uploaded = False
+                for j in range(3):
+                    if owners[j] == rank:
+                        ctx.check(L.b2z_r1cs_coset_evals(ctx.handle, cm._handle, j, None if uploaded else hp(zt),
+                                                         hp(bufs[j])))
+                        uploaded = True
+                works = [dist.broadcast(bufs[j], src=owners[j], async_op=True) for j in range(3)]
+                ctx.check(L.b2z_groth16_shard_begin(ctx.handle, spk._handle, cm._handle, None if uploaded else hp(zt),
+                                                    p(rs[0:1]), p(rs[1:2])))
+                for w in works:
+                    w.wait()
+                torch.cuda.current_stream().synchronize()      # the library works on its own streams
+                ctx.check(L.b2z_groth16_shard_finish(ctx.handle, spk._handle, hp(bufs[0]), hp(bufs[1]), hp(bufs[2]),
+                                                     p(part)))
+                dist.all_gather(gathered, torch.from_numpy(part).cuda())
+                out["proof"] = pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered])
+                proof[:] = np.frombuffer(out["proof"], dtype=np.uint8)
+            step_value = lambda: step(z_dev)
+            step_e2e = lambda: step(z_host)
+            collective = ("3 NCCL broadcasts of %d MB (coset evaluations) + all_gather of %d B per rank"
+                          % (n * 32 // (1 << 20), pkg._ffi.PARTIAL_BYTES))
+
+        # ---- correctness of what is being timed (outside the timed region)
+        step_value()
+        first = proof.tobytes()
+        step_e2e()
+        assert proof.tobytes() == first, "resident and host-buffer paths disagree"
+        res["proof_sha"] = hashlib.sha256(first).hexdigest()[:16]
+
+        for _ in range(warmup):
+            step_value()
+        launches0 = L.b2z_kernel_launches(ctx.handle)
+        L.b2z_profile_enable(ctx.handle, 1)
+        clocks = ClockSampler(self.local_rank)
+        clocks.start()
+        dev_s, wall_s = self.timed(step_value, steps)
+        clk = clocks.stop()
+        launches = L.b2z_kernel_launches(ctx.handle) - launches0
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_uint64 * 8)()
+        units = (ctypes.c_uint64 * 8)()
+        ctx.check(L.b2z_profile_read(ctx.handle, ms, cnt, units, 1))
+        L.b2z_profile_enable(ctx.handle, 0)
+        for _ in range(warmup):
+            step_e2e()
+        e2e_dev_s, e2e_wall_s = self.timed(step_e2e, steps)
+        log("value %.3f ms/proof, e2e %.3f ms/proof" % (dev_s / steps * 1e3, e2e_dev_s / steps * 1e3))
+
+        # ---- replicas (N > 1): one independent proof per GPU, no data-path collective
+        replicas = None
+        if world > 1 and main:
+            pk.free()
+            fpk = pkg.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                                 pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                                 pk.beta_g2, pk.delta_g2).upload(ctx)
+            rr, ss = proof_scalars(rank)                                      # each rank proves with its own r, s
+            rs2 = codec.fr_to_mont_limbs([rr, ss])
+            own = np.zeros(192, dtype=np.uint8)
+
+            def step_rep():
+                ctx.check(L.b2z_groth16_prove_r1cs(ctx.handle, fpk._handle, cm._handle, hp(z_host), p(rs2[0:1]),
+                                                   p(rs2[1:2]), p(own)))
+            for _ in range(warmup):
+                step_rep()
+            rep_s, _ = self.timed(step_rep, steps)
+            replicas = {"proofs_per_s": world * steps / rep_s, "ms_per_proof_per_gpu": rep_s / steps * 1e3,
+                        "scaling": "weak", "call": "b2z_groth16_prove_r1cs, z in pinned host memory",
+                        "collective": "none"}
+            fpk.free()
+            pk = None
+
+        # ---- sharded proof == single-GPU proof?  (rank 0 recomputes it on the whole key; small workloads only,
+        # the big one is checked against the CPU oracle in tests/ and by `replicas` proving the same circuit)
+        if world > 1 and not main:
+            wpk = pkg.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                                 pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                                 pk.beta_g2, pk.delta_g2)
+            pk.free()
+            wpk.upload(ctx)
+            ref = np.zeros(192, dtype=np.uint8)
+            ctx.check(L.b2z_groth16_prove_r1cs(ctx.handle, wpk._handle, cm._handle, hp(z_host), p(rs[0:1]), p(rs[1:2]),
+                                               p(ref)))
+            assert ref.tobytes() == first, "sharded proof differs from the single-GPU proof"
+            res["bytes_equal_single_gpu"] = True
+            wpk.free()
+            pk = None
+
+        per_step = dev_s / steps
+        res.update({
+            "config": config_of(name, inst, world), "value": 1.0 / per_step, "ms_per_step": per_step * 1e3,
+            "wall_ms_per_step": wall_s / steps * 1e3, "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": steps / e2e_dev_s, "unit": "proofs/s", "ms_per_step": e2e_dev_s / steps * 1e3,
+                    "h2d_bytes_per_step": int(m * 32 + 64) * world, "d2h_bytes_per_step": 1344 * world,
+                    "call": ("b2z_groth16_prove_r1cs" if world == 1 else
+                             "b2z_r1cs_coset_evals + b2z_groth16_shard_begin/finish + b2z_groth16_combine on every rank")
+                            + ", z in pinned host memory (row evaluation + witness map + 5 MSMs + host epilogue)"},
+            "collective": collective, "replicas": replicas,
+        })
+        if rank != 0:
+            if pk is not None:
+                pk.free()
+            cm.free()
+            return res
+        # ---- rooflines (rank 0)
+        res["roofline"], res["phase_spans"] = self.rooflines(ms, cnt, units, steps, n, m)
+
+        # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
+        if world == 1 and self.args.cpu_steps > 0 and main:
+            from oracle import cpu_oracle
+            a, b, c = pkg.LibsnarkReduction.constraint_evaluations_device(ctx, cm, z)
+            cpk = cpu_oracle.CpuProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
+                                           pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
+                                           pk.beta_g2, pk.delta_g2)
+            cores = cpu_oracle.hardware_threads()
+            cpu_oracle.set_threads(cores)
+            t0 = time.perf_counter()
+            for _ in range(self.args.cpu_steps):
+                cpu_proof = cpk.prove(a, b, c, z, rs[0], rs[1])
+            cdt = (time.perf_counter() - t0) / self.args.cpu_steps
+            assert cpu_proof == first, "GPU proof bytes differ from the CPU oracle"
+            res["cpu_baseline"] = {"value": 1.0 / cdt, "unit": "proofs/s", "cores": cores, "kind": "port",
+                                   "sample": "%d full proof(s) of the same workload (%.2f s each); proof bytes equal "
+                                             "the GPU's" % (self.args.cpu_steps, cdt)}
+            del cpk
+        key_bytes = self.key_bytes(n, m)
+        res["key_bytes_resident_per_gpu"] = int(key_bytes // world)
+        if pk is not None:
+            pk.free()
+        cm.free()
+        return res
+
+    def key_bytes(self, n, m):
+        L = self.L
+
+        def copies(cnt_pts):
+            c_bits = L.b2z_host_msm_window_bits(cnt_pts, 1)
+            w = (255 + c_bits - 1) // c_bits
+            if 255 - c_bits * (w - 1) > c_bits - 1:
+                w += 1
+            return w
+        return 3 * (m + 2) * 96 * copies(m + 2) + (m + 2) * 192 * copies(m + 2) + n * 96 * copies(n)
+
+    def rooflines(self, ms, cnt, units, steps, n, m):
+        ctx, L = self.ctx, self.L
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        imad = ctypes.c_double()
+        imadw = ctypes.c_double()
+        ctx.check(L.b2z_measure_int_peak(ctx.handle, ctypes.byref(imad), ctypes.byref(imadw)))
+        G1ACC = 3
+        acc_ms = ms[G1ACC] / max(1, cnt[G1ACC])
+        acc_adds = units[G1ACC] / max(1, cnt[G1ACC])
+        # algorithmic integer work (SURVEY.md 8(d)): one XYZZ mixed addition = 10 Fq products = 10 x 600 IMAD-equivalents;
+        # peak = the measured 32-bit IMAD issue rate of this GPU (same run).  Algorithmic bytes: one 96 B affine base +
+        # one 4 B reference per addition.
+        acc_imad = acc_adds * 6000.0
+        acc_bytes = acc_adds * (96 + 4)
+        t = acc_ms * 1e-3
+        roofline = {
+            "kernel": "G1 bucket accumulation (mixed additions of the sorted point references)",
+            "bound": "int", "achieved": acc_imad / t / 1e12 if t else None, "peak": imad.value / 1e12,
+            "unit": "T IMAD-eq/s", "frac": (acc_imad / t / imad.value) if t and imad.value else None,
+            "peak_source": "32-bit IMAD issue rate measured by b2z_measure_int_peak on this GPU in this run",
+            "normaliser": "6000 IMAD-equivalents per G1 mixed addition (10 Fq products x 600; SURVEY.md 8(d), BASELINE.md)",
+            # dram bytes of one launch: constant from the committed ncu --set full capture (profiles/), scaled by adds
+            "traffic": acc_adds * 156.0,
+            "traffic_source": "constant 156 B per mixed addition from the ncu --set full capture under profiles/ "
+                              "(not re-measured per run)",
+            "hbm": {"achieved": acc_bytes / t / 1e9 if t else None, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (acc_bytes / t / 1e9 / hbm_peak) if t else None, "peak_source": hbm_src,
+                    "note": "not the binding roofline: the kernel is integer-pipe bound (SURVEY.md App. C)"},
+            "wide_mac": {"achieved": acc_adds * 3000.0 / t / 1e12 if t else None, "peak": imadw.value / 1e12,
+                         "unit": "T carry-chained 32x32+64 multiply-add/s",
+                         "note": "builder's own probe of the IMAD.WIDE.X form the field product is made of"},
+            "launch_ms": acc_ms, "mixed_adds_per_launch": acc_adds, "launches_timed": int(cnt[G1ACC]),
+        }
+        names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
+        spans = {nm: {"span_ms_per_step": ms[i] / steps, "launches_per_step": cnt[i] / steps,
+                      "units_per_step": units[i] / steps} for i, nm in enumerate(names)}
+        spans["note"] = ("CUDA-event spans on concurrent streams: they OVERLAP and do not add up to ms_per_step; "
+                         "kernel shares are in profiles/*launch_shares*")
+        ntt_el = units[0] / steps
+        spans["ntt_pass"]["hbm_gbs_algorithmic"] = (ntt_el * 64 / (ms[0] / steps * 1e-3) / 1e9) if ms[0] else None
+        spans["ntt_pass"]["int_frac"] = ((ntt_el / 2) * (n.bit_length() - 1) * 272 / (ms[0] / steps * 1e-3) / imad.value
+                                         if ms[0] and imad.value else None)
+        g2_ms = ms[4] / max(1, cnt[4])
+        g2_adds = units[4] / max(1, cnt[4])
+        spans["msm_accum_g2"]["int_frac"] = (g2_adds * 18000.0 / (g2_ms * 1e-3) / imad.value) if g2_ms and imad.value else None
+        return roofline, spans
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -212,243 +499,55 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-steps", type=int, default=2, help="proofs timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-steps", type=int, default=1, help="proofs timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra c2 measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        if args.steps > 3:
-            args.steps = 3                      # bounded sample: a CPU proof takes seconds
-        args.warmup = min(args.warmup, 1)
+        big = args.workload == "c5"
+        args.steps = min(args.steps, 2 if big else 3)       # bounded sample: a CPU proof takes seconds
+        args.warmup = 0 if big else min(args.warmup, 1)
         run_reference(args, rank, world)
         return
     if args.warmup < 3:
         args.warmup = 3
 
-    import numpy as np
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    pkg = importlib.import_module(PKG)
-    codec = pkg.codec
-    ctx = pkg.Context(local_rank)
-    L = ctx._lib
-
-    # ---- workload (outside the timed region)
-    inst = build_instance(args.workload)
-    pk, vk = pkg.Groth16.generate_parameters_with_qap(ctx, inst.cm, inst.num_constraints, inst.num_instance,
-                                                      inst.num_variables, *toxic_waste())
-    pk.upload(ctx)
-    inst.cm.upload(ctx)
-    z = codec.fr_to_mont_limbs(inst.z)
-    a, b, c = pkg.LibsnarkReduction.constraint_evaluations_device(ctx, inst.cm, z)
-    n, m = inst.domain_size, inst.num_variables
-    rnd = random.Random(SEED ^ 1 ^ (rank << 8))      # each rank proves with its own r, s
-    r, s = rnd.randrange(R_MOD), rnd.randrange(R_MOD)
-    rs = codec.fr_to_mont_limbs([r, s])
-    p = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
-    proof = np.zeros(192, dtype=np.uint8)
-
-    def as_torch(x):
-        return torch.from_numpy(x.view(np.int64).copy())
-    # pinned host copies for the end-to-end arm, device copies for the resident arm
-    host = [as_torch(x).pin_memory() for x in (a, b, c, z)]
-    dev0 = [t.cuda() for t in host]
-    dev = [torch.empty_like(t) for t in dev0[:3]] + [dev0[3]]
-    hp = lambda t: ctypes.c_void_p(t.data_ptr())
-
-    def step_resident():
-        for d, s0 in zip(dev[:3], dev0[:3]):
-            d.copy_(s0, non_blocking=True)             # the witness map clobbers a, b, c
-        st = L.b2z_groth16_prove_device(ctx.handle, pk._handle, hp(dev[0]), hp(dev[1]), hp(dev[2]), hp(dev[3]),
-                                        p(rs[0:1]), p(rs[1:2]), p(proof))
-        ctx.check(st)
-
-    def step_e2e():
-        # the call a user of the reference makes: assignment in host memory -> 192 proof bytes; the
-        # constraint rows are evaluated on the GPU from the uploaded matrices (b2z_groth16_prove_r1cs)
-        st = L.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, inst.cm._handle, hp(host[3]), p(rs[0:1]), p(rs[1:2]),
-                                      p(proof))
-        ctx.check(st)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        w0 = time.perf_counter()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - w0
-        dev_s = e0.elapsed_time(e1) * 1e-3
-        t = torch.tensor([max(dev_s, 0.0), wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
-
-    # ---- correctness of what is being timed (not in the timed region)
-    step_resident()
-    first = proof.tobytes()
-    step_e2e()
-    assert proof.tobytes() == first, "resident and host-buffer paths disagree"
-
-    for _ in range(args.warmup):
-        step_resident()
-    launches0 = L.b2z_kernel_launches(ctx.handle)
-    print("[bench] library kernels launched before the timed region: %d" % launches0, file=sys.stderr, flush=True)
-    L.b2z_profile_enable(ctx.handle, 1)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    dev_s, wall_s = timed(step_resident, args.steps)
-    clk = clocks.stop()
-    launches = L.b2z_kernel_launches(ctx.handle) - launches0
-    ms = (ctypes.c_double * 8)()
-    cnt = (ctypes.c_uint64 * 8)()
-    units = (ctypes.c_uint64 * 8)()
-    ctx.check(L.b2z_profile_read(ctx.handle, ms, cnt, units, 1))
-    L.b2z_profile_enable(ctx.handle, 0)
-    for _ in range(args.warmup):
-        step_e2e()
-    e2e_dev_s, e2e_wall_s = timed(step_e2e, args.steps)
-
-    # ---- point-sharded mode (N > 1): ONE proof computed by all ranks -- reported next to
-    # the weak-scaling line; every rank holds 1/N of every base set, partial sums travel over NCCL
-    sharded = None
+    b = Bench(args, rank, local_rank, world)
+    res = b.measure(args.workload, args.steps, args.warmup, main=True)
+    extra = {}
+    if not args.no_extra and args.workload != "c2":
+        e = b.measure("c2", max(args.steps, 10), args.warmup, main=False)
+        if rank == 0:
+            extra["c2"] = {k: e[k] for k in ("config", "value", "ms_per_step", "e2e", "gpu_launches", "roofline",
+                                             "collective", "bytes_equal_single_gpu", "proof_sha") if k in e}
+    if rank == 0:
+        line = {
+            "metric": "groth16_proofs_per_sec", "value": res["value"], "unit": "proofs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": res["config"], "clocks": res["clocks"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"],
+            "wall_ms_per_step": res["wall_ms_per_step"], "roofline": res["roofline"],
+            "cpu_baseline": res.get("cpu_baseline"), "phase_spans": res["phase_spans"],
+            "collective": res["collective"], "replicas": res["replicas"],
+            "key_bytes_resident_per_gpu": res.get("key_bytes_resident_per_gpu"), "proof_sha": res["proof_sha"],
+            "extra": extra,
+        }
+        emit(line)
     if world > 1:
-        spk = pkg.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
-                             pk.b_g2_query, pk.h_query, pk.l_query, pk.alpha_g1, pk.beta_g1, pk.delta_g1,
-                             pk.beta_g2, pk.delta_g2).upload(ctx, rank=rank, world=world)
-        r0, s0 = 0x1234567, 0x7654321             # the same r, s on every rank
-        rs0 = codec.fr_to_mont_limbs([r0, s0])
-        part = np.zeros(pkg._ffi.PARTIAL_BYTES, dtype=np.uint8)
-        gathered = [torch.empty(pkg._ffi.PARTIAL_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        out = {}
-
-        def step_sharded():
-            ctx.check(L.b2z_groth16_prove_partial_r1cs(ctx.handle, spk._handle, inst.cm._handle, hp(host[3]),
-                                                       p(rs0[0:1]), p(rs0[1:2]), p(part)))
-            dist.all_gather(gathered, torch.from_numpy(part).cuda())
-            out["proof"] = pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered])
-
-        step_sharded()
-        ref = np.zeros(192, dtype=np.uint8)
-        ctx.check(L.b2z_groth16_prove_r1cs(ctx.handle, pk._handle, inst.cm._handle, hp(host[3]), p(rs0[0:1]),
-                                           p(rs0[1:2]), p(ref)))
-        assert out["proof"] == ref.tobytes(), "sharded proof differs from the single-GPU proof"
-        for _ in range(args.warmup):
-            step_sharded()
-        sh_dev_s, sh_wall_s = timed(step_sharded, args.steps)
-        sharded = {"ms_per_proof": sh_dev_s / args.steps * 1e3, "proofs_per_s": args.steps / sh_dev_s,
-                   "scaling": "strong", "collective": "all_gather of %d B per rank (NCCL)" % pkg._ffi.PARTIAL_BYTES,
-                   "bytes_equal_single_gpu": True}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- rooflines
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    imad = ctypes.c_double()
-    imadw = ctypes.c_double()
-    ctx.check(L.b2z_measure_int_peak(ctx.handle, ctypes.byref(imad), ctypes.byref(imadw)))
-    G1ACC = 3
-    acc_ms = ms[G1ACC] / max(1, cnt[G1ACC])
-    acc_adds = units[G1ACC] / max(1, cnt[G1ACC])
-    # algorithmic bytes of one G1 accumulation launch: one 96 B affine base + one 4 B reference per mixed addition
-    acc_bytes = acc_adds * (96 + 4)
-    # algorithmic integer work: XYZZ mixed addition = 10 Fq products = 10 * 300 32x32+64 multiply-adds
-    acc_macs = acc_adds * 3000.0
-    roofline = {
-        "kernel": "msm_accum_kernel<G1> (bucket accumulation, XYZZ mixed additions)",
-        "bound": "hbm", "achieved": acc_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else None, "peak": hbm_peak,
-        "unit": "GB/s", "frac": (acc_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak) if acc_ms else None,
-        # dram__bytes_read+write of one G1 accumulation launch from the committed ncu --set full capture
-        # (profiles/r01_ncu/prof_accum_g1.raw.csv: 245.8 MB read + 8.6 MB written by the 1.63 M-addition launch of
-        # the A query = 156 B per mixed addition, 1.56x the algorithmic 100 B), scaled to this run's average launch
-        "traffic": acc_adds * 156.0,
-        "peak_source": hbm_src,
-        "note": "this kernel is integer-pipe bound, not HBM bound (SURVEY.md App. C): see int_pipe",
-        "int_pipe": {
-            "achieved": acc_macs / (acc_ms * 1e-3) / 1e12 if acc_ms else None, "peak": imadw.value / 1e12,
-            "unit": "T multiply-add/s (32x32+64, carry-chained IMAD.WIDE)",
-            "frac": (acc_macs / (acc_ms * 1e-3) / imadw.value) if acc_ms and imadw.value else None,
-            "peak_source": "b2z_measure_int_peak on this GPU, same run", "imad_32_peak": imad.value / 1e12},
-        "launch_ms": acc_ms, "mixed_adds_per_launch": acc_adds, "launches_timed": int(cnt[G1ACC]),
-    }
-    phase_names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
-    phases = {nm: {"ms_per_step": ms[i] / args.steps, "launches_per_step": cnt[i] / args.steps,
-                   "units_per_step": units[i] / args.steps} for i, nm in enumerate(phase_names)}
-    ntt_el = units[0] / args.steps
-    phases["ntt_pass"]["hbm_gbs_algorithmic"] = (ntt_el * 64 / (ms[0] / args.steps * 1e-3) / 1e9) if ms[0] else None
-
-    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only)
-    cpu = None
-    if world == 1 and args.cpu_steps > 0:
-        cpu_oracle, cpk = cpu_prove_setup(pkg, inst, pk)
-        cores = cpu_oracle.hardware_threads()
-        cpu_oracle.set_threads(cores)
-        t0 = time.perf_counter()
-        for _ in range(args.cpu_steps):
-            cpu_proof = cpk.prove(a, b, c, z, rs[0], rs[1])
-        cdt = (time.perf_counter() - t0) / args.cpu_steps
-        assert cpu_proof == first, "GPU proof bytes differ from the CPU oracle"
-        cpu = {"value": 1.0 / cdt, "unit": "proofs/s", "cores": cores, "kind": "port",
-               "sample": "%d full proofs of the same workload (%.2f s each); proof bytes equal the GPU's"
-                         % (args.cpu_steps, cdt)}
-
-    def copies(cnt_pts):
-        c_bits = L.b2z_host_msm_window_bits(cnt_pts, 1)
-        w = (255 + c_bits - 1) // c_bits
-        if 255 - c_bits * (w - 1) > c_bits - 1:
-            w += 1
-        return w
-    key_bytes = (3 * (m + 2) * 96 * copies(m + 2) + (m + 2) * 192 * copies(m + 2) + n * 96 * copies(n))
-
-    per_step = dev_s / args.steps
-    value = world / per_step
-    e2e_val = world / (e2e_dev_s / args.steps)
-    line = {
-        "metric": "groth16_proofs_per_sec", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 limbs (Fr 255-bit / Fq 381-bit integers)", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "num_constraints": inst.num_constraints, "domain": n,
-                   "num_variables": m, "parallelism": "one independent proof per GPU" if world > 1 else "1 GPU",
-                   "cache_policy": "inputs larger than L2: every step streams %.0f MB of key bases "
-                                   "(> 126 MB L2) plus %.1f MB of a/b/c/z; no explicit flush" %
-                                   (key_bytes / 1e6, (3 * n + m) * 32 / 1e6)},
-        "clocks": clk,
-        "e2e": {"value": e2e_val, "unit": "proofs/s", "ms_per_step": e2e_dev_s / args.steps * 1e3,
-                "h2d_bytes_per_step": int(m * 32 + 64), "d2h_bytes_per_step": 1344,
-                "call": "b2z_groth16_prove_r1cs (row evaluation + witness map + 4 MSMs + host epilogue)"},
-        "gpu_launches": int(launches),
-        "wall_ms_per_step": wall_s / args.steps * 1e3,
-        "roofline": roofline, "phases": phases, "cpu_baseline": cpu, "sharded_single_proof": sharded,
-        "proof_sha": __import__("hashlib").sha256(first).hexdigest()[:16],
-    }
-    emit(line)
-    if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
+    b.ctx.close()
 
 
 if __name__ == "__main__":

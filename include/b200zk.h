@@ -20,8 +20,16 @@
  *
  * Threading: a b2z_ctx serialises the calls made on it (internal mutex); use one
  * ctx per host thread (actix worker, /root/reference/src/main.rs:37) for
- * concurrency.  Errors never unwind across the boundary: every call returns a
- * b2z_status and b2z_last_error() describes the most recent failure on that ctx.
+ * concurrency.  A b2z_pk / b2z_r1cs handle holds per-proof device scratch and
+ * therefore BELONGS TO THE CONTEXT IT WAS UPLOADED THROUGH: passing it to any
+ * other context returns B2Z_EINVAL (upload one copy per context / worker).
+ * Errors never unwind across the boundary: every call returns a b2z_status and
+ * b2z_last_error() describes the most recent failure on that ctx.
+ *
+ * Assignment pointers (`z`) of the *_r1cs and shard entry points may be host
+ * pointers (pageable or page-locked) or device pointers on the context's device
+ * (the copy uses cudaMemcpyDefault); a device buffer must be complete when the
+ * call is made.
  */
 #ifndef B200ZK_H_
 #define B200ZK_H_
@@ -78,7 +86,9 @@ B2Z_API b2z_status b2z_witness_map(b2z_ctx* ctx, const uint64_t* a, const uint64
 /* ---- ark_ec::VariableBaseMSM::msm_bigint --------------------------------------
  * for G1Projective / G2Projective (called five times per proof by
  * create_proof_with_assignment).  bases: n affine points; scalars: n canonical
- * bigints; out: one Jacobian point (18 / 36 limbs), canonical Montgomery limbs.   */
+ * bigints < 2^255 (into_bigint() of an Fr element; anything larger is rejected
+ * with B2Z_EINVAL); out: one Jacobian point (18 / 36 limbs), canonical Montgomery
+ * limbs.                                                                          */
 B2Z_API b2z_status b2z_msm_g1(b2z_ctx* ctx, const uint64_t* bases, const uint8_t* inf_bitmap,
                       const uint64_t* scalars, uint64_t n, uint64_t out_xyz[18]);
 B2Z_API b2z_status b2z_msm_g2(b2z_ctx* ctx, const uint64_t* bases, const uint8_t* inf_bitmap,
@@ -172,8 +182,10 @@ B2Z_API b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk
 B2Z_API b2z_status b2z_groth16_combine(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]);
 
 /* Same computation on inputs already resident in device memory (device pointers
- * on ctx's device; a/b/c are clobbered).  Used to separate kernel time from
- * PCIe time in benchmarks; the proof bytes still land in host memory.            */
+ * on ctx's device; a/b/c are clobbered).  The buffers must be complete, or have
+ * been produced on the legacy default stream (the library orders its own streams
+ * after that stream; it does not synchronise the device).  The proof bytes still
+ * land in host memory.                                                           */
 B2Z_API b2z_status b2z_groth16_prove_device(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_a,
                                     uint64_t* d_b, uint64_t* d_c, const uint64_t* d_z,
                                     const uint64_t r[4], const uint64_t s[4],
@@ -222,8 +234,10 @@ B2Z_API b2z_status b2z_measure_int_peak(b2z_ctx* ctx, double* imad_per_s, double
  *   - every rank:        b2z_groth16_shard_finish(ctx, pk_shard, d_a, d_b, d_c, partial_out)
  *        pointwise quotient, last transform, this shard's H sum, host epilogue: B2Z_PARTIAL_BYTES as from
  *        b2z_groth16_prove_partial (d_a is clobbered).  Combine with b2z_groth16_combine.
- * z: the assignment in host memory for the FIRST of these calls of a proof (it is uploaded once), NULL afterwards.
- * A rank must not start another proof on the same key / r1cs before shard_finish.                               */
+ * z: the assignment for the FIRST of these calls of a proof (it is uploaded once), NULL afterwards -- NULL is only
+ * accepted inside one proof: shard_finish invalidates the uploaded assignment, so a mis-sequenced call fails with
+ * B2Z_EINVAL instead of proving a stale one.  A rank must not start another proof on the same key / r1cs (nor free
+ * the r1cs) before shard_finish.                                                                                  */
 B2Z_API b2z_status b2z_groth16_shard_begin(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r1cs, const uint64_t* z,
                                            const uint64_t r[4], const uint64_t s[4]);
 B2Z_API b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r1cs, uint32_t which, const uint64_t* z,

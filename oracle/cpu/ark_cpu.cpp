@@ -24,6 +24,9 @@
 // Constants are derived at start-up from the two moduli only.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -524,6 +527,102 @@ static Jac<F> calculate_coeff(const Jac<F>& initial, const std::vector<Affine<F>
   return res.add_mixed(vk_param);
 }
 
+
+// ------------------------------------------------------------------ ark-ec FixedBase::msm (key generation)
+// out[i] = k_i * G for canonical scalars k_i: unsigned 8-bit windows over per-window tables
+// table[w][d] = d * 2^(8w) G, Jacobian mixed additions, one batched normalisation per thread chunk
+// (ark-groth16's generator calls FixedBase::msm for every query array; reference call sites
+// src/arkworks/backend/matrix_proof.rs:128-131, fibbonaci_handler.rs:107).
+template <class F>
+struct FixedBaseTable {
+  std::vector<Affine<F>> t;   // 32 x 256
+  explicit FixedBaseTable(const Affine<F>& g) : t(32 * 256) {
+    std::vector<Jac<F>> j(32 * 256);
+    Jac<F> base{g.x, g.y, F::one()};
+    for (int w = 0; w < 32; w++) {
+      Jac<F> acc = Jac<F>::identity();
+      for (int d = 0; d < 256; d++) {
+        j[w * 256 + d] = acc;
+        acc = acc.add(base);
+      }
+      base = acc;   // 256 * base
+    }
+    parallel_for(j.size(), [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) t[i] = j[i].to_affine(); });
+  }
+};
+
+template <class F>
+static void batch_to_affine(const Jac<F>* in, Affine<F>* out, size_t n) {
+  // Montgomery's trick on the z coordinates
+  std::vector<F> pref(n);
+  F acc = F::one();
+  for (size_t i = 0; i < n; i++) {
+    pref[i] = acc;
+    if (!in[i].is_identity()) acc = acc * in[i].z;
+  }
+  F inv = acc.inverse();
+  for (size_t i = n; i-- > 0;) {
+    if (in[i].is_identity()) { out[i] = Affine<F>{F::zero(), F::zero(), true}; continue; }
+    const F zi = inv * pref[i];
+    inv = inv * in[i].z;
+    const F zi2 = zi.sqr();
+    out[i] = Affine<F>{in[i].x * zi2, in[i].y * zi2 * zi, false};
+  }
+}
+
+template <class F>
+static void fixed_base_msm(const FixedBaseTable<F>& tab, const u64* scalars, size_t n, Affine<F>* out) {
+  parallel_for(n, [&](size_t b, size_t e) {
+    const size_t kChunk = 1024;
+    std::vector<Jac<F>> tmp(kChunk);
+    for (size_t s0 = b; s0 < e; s0 += kChunk) {
+      const size_t cnt = std::min(kChunk, e - s0);
+      for (size_t i = 0; i < cnt; i++) {
+        const u64* k = scalars + 4 * (s0 + i);
+        Jac<F> acc = Jac<F>::identity();
+        for (int w = 0; w < 32; w++) {
+          const unsigned d = (unsigned)(k[w >> 3] >> ((w & 7) * 8)) & 0xff;
+          if (d) acc = acc.add_mixed(tab.t[w * 256 + d]);
+        }
+        tmp[i] = acc;
+      }
+      batch_to_affine<F>(tmp.data(), out + s0, cnt);
+    }
+  });
+}
+
+static void store_g1(u64* limbs, uint8_t* inf, const std::vector<Affine<Fq>>& v) {
+  if (inf) memset(inf, 0, (v.size() + 7) / 8);
+  for (size_t i = 0; i < v.size(); i++) {
+    memcpy(limbs + 12 * i, v[i].x.l, 48);
+    memcpy(limbs + 12 * i + 6, v[i].y.l, 48);
+    if (v[i].inf && inf) inf[i >> 3] |= (uint8_t)(1u << (i & 7));
+  }
+}
+static void store_g2(u64* limbs, uint8_t* inf, const std::vector<Affine<Fq2>>& v) {
+  if (inf) memset(inf, 0, (v.size() + 7) / 8);
+  for (size_t i = 0; i < v.size(); i++) {
+    memcpy(limbs + 24 * i, v[i].x.c0.l, 48);
+    memcpy(limbs + 24 * i + 6, v[i].x.c1.l, 48);
+    memcpy(limbs + 24 * i + 12, v[i].y.c0.l, 48);
+    memcpy(limbs + 24 * i + 18, v[i].y.c1.l, 48);
+    if (v[i].inf && inf) inf[i >> 3] |= (uint8_t)(1u << (i & 7));
+  }
+}
+
+static Fr fr_from_canonical(const u64* c) {
+  Fr x, r2;
+  memcpy(x.l, c, 32);
+  memcpy(r2.l, g_fr.r2, 32);
+  return x * r2;
+}
+
+struct Csr {
+  const u64* rp;
+  const uint32_t* ci;
+  const u64* cf;   // Montgomery limbs, 4 per entry
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------ C entry points (ctypes)
@@ -634,6 +733,163 @@ void ark_cpu_prove(const ark_cpu_pk* pk, u64* a, u64* b, u64* c, const u64* z, c
   ser_g1(proof_out, g_a.to_affine());
   ser_g2(proof_out + 48, g2_b.to_affine());
   ser_g1(proof_out + 144, g_c.to_affine());
+}
+
+
+// ark-groth16 generator.rs generate_parameters_with_qap::<LibsnarkReduction> with caller-supplied toxic waste and
+// generators (Groth16::setup / circuit_specific_setup draw these from the rng: matrix_proof.rs:128-131).
+//   matrices: CSR (row_ptr u64[nc + 1], cols u32, coeffs Montgomery limbs); toxic: alpha, beta, gamma, delta, tau as
+//   canonical 4-limb integers; g1_gen / g2_gen: affine generators, Montgomery limbs.
+//   outputs (caller-allocated): the ProvingKey arrays in the layout of b2z_pk_desc plus gamma_g2 and gamma_abc_g1.
+int ark_cpu_groth16_setup(u64 nc, u64 l, u64 m, const u64* a_rp, const uint32_t* a_ci, const u64* a_cf, const u64* b_rp,
+                          const uint32_t* b_ci, const u64* b_cf, const u64* c_rp, const uint32_t* c_ci, const u64* c_cf,
+                          const u64* toxic, const u64* g1_gen, const u64* g2_gen, u64* a_q, uint8_t* a_inf, u64* b1_q,
+                          uint8_t* b1_inf, u64* b2_q, uint8_t* b2_inf, u64* h_q, uint8_t* h_inf, u64* l_q, uint8_t* l_inf,
+                          u64* alpha_g1, u64* beta_g1, u64* delta_g1, u64* beta_g2, u64* gamma_g2, u64* delta_g2,
+                          u64* gamma_abc, uint8_t* gamma_abc_inf) {
+  uint32_t log_n = 0;
+  while (((u64)1 << log_n) < nc + l) log_n++;
+  if (log_n > 32) return 2;
+  const size_t n = (size_t)1 << log_n;
+  const bool verbose = getenv("ARK_CPU_VERBOSE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    auto now = std::chrono::steady_clock::now();
+    if (verbose) fprintf(stderr, "[ark_cpu setup] %-12s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+    t_last = now;
+  };
+  const Fr alpha = fr_from_canonical(toxic), beta = fr_from_canonical(toxic + 4), gamma = fr_from_canonical(toxic + 8),
+           delta = fr_from_canonical(toxic + 12), tau = fr_from_canonical(toxic + 16);
+  Domain d(log_n);
+  // evaluate_all_lagrange_coefficients(tau): L_i = Z(tau)/n * w^i / (tau - w^i)
+  Fr tn = tau;
+  for (uint32_t i = 0; i < log_n; i++) tn = tn.sqr();
+  const Fr zt = tn - Fr::one();
+  if (zt.is_zero()) return 1;
+  std::vector<Fr> lag(n), den(n);
+  parallel_for(n, [&](size_t b, size_t e) {
+    u64 eb[1] = {(u64)b};
+    Fr w = d.gen.pow(eb, 1);
+    for (size_t i = b; i < e; i++) { lag[i] = w; den[i] = tau - w; w = w * d.gen; }
+  });
+  parallel_for(n, [&](size_t b, size_t e) {   // batch inversion per chunk
+    std::vector<Fr> pref(e - b);
+    Fr acc = Fr::one();
+    for (size_t i = b; i < e; i++) { pref[i - b] = acc; acc = acc * den[i]; }
+    Fr inv = acc.inverse();
+    const Fr zn = zt * d.size_inv;
+    for (size_t i = e; i-- > b;) {
+      const Fr di = inv * pref[i - b];
+      inv = inv * den[i];
+      lag[i] = zn * lag[i] * di;
+    }
+  });
+  lap("lagrange");
+  // instance_map_with_evaluation: a_i(tau), b_i(tau), c_i(tau) per variable
+  std::vector<Fr> at(m, Fr::zero()), bt(m, Fr::zero()), ct(m, Fr::zero());
+  for (u64 j = 0; j < l; j++) at[j] = lag[nc + j];
+  const Csr mats[3] = {{a_rp, a_ci, a_cf}, {b_rp, b_ci, b_cf}, {c_rp, c_ci, c_cf}};
+  std::vector<Fr>* outs[3] = {&at, &bt, &ct};
+  {
+    std::vector<std::thread> pool;   // one thread per matrix: column scatter is not row-parallel
+    for (int k = 0; k < 3; k++)
+      pool.emplace_back([&, k] {
+        const Csr& M = mats[k];
+        std::vector<Fr>& o = *outs[k];
+        for (u64 i = 0; i < nc; i++)
+          for (u64 e = M.rp[i]; e < M.rp[i + 1]; e++) {
+            Fr cf;
+            memcpy(cf.l, M.cf + 4 * e, 32);
+            o[M.ci[e]] = o[M.ci[e]] + lag[i] * cf;
+          }
+      });
+    for (auto& th : pool) th.join();
+  }
+  lap("qap");
+  const Fr ginv = gamma.inverse(), dinv = delta.inverse();
+  auto canon = [](const std::vector<Fr>& v) {
+    std::vector<u64> out(4 * v.size());
+    parallel_for(v.size(), [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) v[i].to_canonical(&out[4 * i]); });
+    return out;
+  };
+  Affine<Fq> g1;
+  memcpy(g1.x.l, g1_gen, 48); memcpy(g1.y.l, g1_gen + 6, 48); g1.inf = false;
+  Affine<Fq2> g2;
+  memcpy(g2.x.c0.l, g2_gen, 48); memcpy(g2.x.c1.l, g2_gen + 6, 48);
+  memcpy(g2.y.c0.l, g2_gen + 12, 48); memcpy(g2.y.c1.l, g2_gen + 18, 48); g2.inf = false;
+  const FixedBaseTable<Fq> t1(g1);
+  const FixedBaseTable<Fq2> t2(g2);
+  lap("tables");
+  auto mul1 = [&](const std::vector<Fr>& v, u64* out, uint8_t* inf) {
+    std::vector<u64> k = canon(v);
+    std::vector<Affine<Fq>> pts(v.size());
+    fixed_base_msm<Fq>(t1, k.data(), v.size(), pts.data());
+    store_g1(out, inf, pts);
+  };
+  auto mul2 = [&](const std::vector<Fr>& v, u64* out, uint8_t* inf) {
+    std::vector<u64> k = canon(v);
+    std::vector<Affine<Fq2>> pts(v.size());
+    fixed_base_msm<Fq2>(t2, k.data(), v.size(), pts.data());
+    store_g2(out, inf, pts);
+  };
+  mul1(at, a_q, a_inf);
+  lap("a_query");
+  mul1(bt, b1_q, b1_inf);
+  lap("b_g1_query");
+  mul2(bt, b2_q, b2_inf);
+  lap("b_g2_query");
+  {
+    std::vector<Fr> hs(n - 1);
+    parallel_for(n - 1, [&](size_t b, size_t e) {
+      u64 eb[1] = {(u64)b};
+      Fr t = zt * dinv * tau.pow(eb, 1);
+      for (size_t i = b; i < e; i++) { hs[i] = t; t = t * tau; }
+    });
+    mul1(hs, h_q, h_inf);
+    lap("h_query");
+  }
+  std::vector<Fr> abc(m);
+  parallel_for(m, [&](size_t b, size_t e) { for (size_t i = b; i < e; i++) abc[i] = beta * at[i] + alpha * bt[i] + ct[i]; });
+  {
+    std::vector<Fr> lq(m - l), gq(l);
+    for (u64 i = l; i < m; i++) lq[i - l] = abc[i] * dinv;
+    for (u64 i = 0; i < l; i++) gq[i] = abc[i] * ginv;
+    mul1(lq, l_q, l_inf);
+    mul1(gq, gamma_abc, gamma_abc_inf);
+  }
+  uint8_t dummy[1];
+  mul1(std::vector<Fr>{alpha}, alpha_g1, dummy);
+  mul1(std::vector<Fr>{beta}, beta_g1, dummy);
+  mul1(std::vector<Fr>{delta}, delta_g1, dummy);
+  mul2(std::vector<Fr>{beta}, beta_g2, dummy);
+  mul2(std::vector<Fr>{gamma}, gamma_g2, dummy);
+  mul2(std::vector<Fr>{delta}, delta_g2, dummy);
+  lap("l, vk");
+  return 0;
+}
+
+// constraint-row evaluation (the evaluate_constraint loop of witness_map_from_matrices), threads over rows
+void ark_cpu_constraint_evals(u64 nc, u64 l, uint32_t log_n, const u64* a_rp, const uint32_t* a_ci, const u64* a_cf,
+                              const u64* b_rp, const uint32_t* b_ci, const u64* b_cf, const u64* c_rp,
+                              const uint32_t* c_ci, const u64* c_cf, const u64* z, u64* a_out, u64* b_out, u64* c_out) {
+  const size_t n = (size_t)1 << log_n;
+  memset(a_out, 0, 32 * n); memset(b_out, 0, 32 * n); memset(c_out, 0, 32 * n);
+  const Csr mats[3] = {{a_rp, a_ci, a_cf}, {b_rp, b_ci, b_cf}, {c_rp, c_ci, c_cf}};
+  u64* outs[3] = {a_out, b_out, c_out};
+  const Fr* zz = reinterpret_cast<const Fr*>(z);
+  for (int k = 0; k < 3; k++)
+    parallel_for(nc, [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) {
+        Fr acc = Fr::zero();
+        for (u64 t = mats[k].rp[i]; t < mats[k].rp[i + 1]; t++) {
+          Fr cf;
+          memcpy(cf.l, mats[k].cf + 4 * t, 32);
+          acc = acc + cf * zz[mats[k].ci[t]];
+        }
+        memcpy(outs[k] + 4 * i, acc.l, 32);
+      }
+    });
+  memcpy(a_out + 4 * nc, z, 32 * l);
 }
 
 }  // extern "C"

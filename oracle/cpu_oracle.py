@@ -14,16 +14,40 @@ _lib = None
 vp = ctypes.c_void_p
 
 
-def build():
+_STAMP = os.path.join(_HERE, "cpu", "libark_cpu.host")
+
+
+def _host_signature():
+    """-march=native ties the binary to the CPU it was built on (the CPU baseline is
+    compiled for the host it is timed on): the ISA flag set of this machine."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.sha256(" ".join(sorted(line.split(":", 1)[1].split())).encode()).hexdigest()[:16]
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force=False):
+    """make -C oracle; rebuilt when the library was compiled on a different CPU (the .so travels to the
+    GPU box with the repo snapshot, the box has the same toolchain)."""
+    sig = _host_signature()
+    have = open(_STAMP).read().strip() if os.path.exists(_STAMP) else ""
+    if force or have != sig:
+        subprocess.run(["make", "-C", _HERE, "-s", "clean"], check=True)
     subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    with open(_STAMP, "w") as f:
+        f.write(sig)
     return _LIB_PATH
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB_PATH):
-            build()
+        build()                    # no-op when up to date and built for this CPU
         L = ctypes.CDLL(_LIB_PATH)
         L.ark_cpu_set_threads.argtypes = [ctypes.c_int]
         L.ark_cpu_hardware_threads.restype = ctypes.c_int
@@ -37,6 +61,9 @@ def lib():
         L.ark_cpu_pk_new.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32] + [vp] * 15
         L.ark_cpu_pk_free.argtypes = [vp]
         L.ark_cpu_prove.argtypes = [vp] * 8
+        L.ark_cpu_groth16_setup.restype = ctypes.c_int
+        L.ark_cpu_groth16_setup.argtypes = [ctypes.c_uint64] * 3 + [vp] * 30
+        L.ark_cpu_constraint_evals.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32] + [vp] * 13
         _lib = L
     return _lib
 
@@ -126,3 +153,66 @@ class CpuProvingKey:
                 self.handle = None
         except Exception:
             pass
+
+
+def _gen_limbs():
+    from oracle import bls12_381 as O
+    g1 = np.array(O.int_to_limbs(O.fq_to_mont(O.G1_GEN[0]), 6) + O.int_to_limbs(O.fq_to_mont(O.G1_GEN[1]), 6),
+                  dtype=np.uint64)
+    (x0, x1), (y0, y1) = O.G2_GEN
+    g2 = np.array(sum((O.int_to_limbs(O.fq_to_mont(v), 6) for v in (x0, x1, y0, y1)), []), dtype=np.uint64)
+    return g1, g2
+
+
+class CpuKey:
+    """Arrays of a Groth16 key in the b2z_pk_desc layout (limbs ndarray, identity bitmap) + the vk extras."""
+
+
+def groth16_setup(csr_a, csr_b, csr_c, num_constraints, num_instance, num_variables, toxic):
+    """ark-groth16 generate_parameters_with_qap on the CPU (standard generators, caller-supplied toxic waste
+    alpha, beta, gamma, delta, tau as ints).  csr_*: (row_ptr uint64, cols uint32, coeffs (nnz, 4) Montgomery)."""
+    nc, l, m = int(num_constraints), int(num_instance), int(num_variables)
+    n = 1
+    while n < nc + l:
+        n <<= 1
+    mats = []
+    for rp, ci, cf in (csr_a, csr_b, csr_c):
+        mats += [_c(rp), _c(ci, np.uint32), _c(cf)]
+    tox = np.frombuffer(b"".join(int(t).to_bytes(32, "little") for t in toxic), dtype=np.uint64).copy()
+    g1, g2 = _gen_limbs()
+    k = CpuKey()
+    k.num_variables, k.num_instance, k.domain_size = m, l, n
+    z1 = lambda cnt: (np.zeros((cnt, 12), np.uint64), np.zeros((cnt + 7) // 8 + 1, np.uint8))
+    z2 = lambda cnt: (np.zeros((cnt, 24), np.uint64), np.zeros((cnt + 7) // 8 + 1, np.uint8))
+    k.a_query, k.b_g1_query, k.b_g2_query, k.h_query, k.l_query = z1(m), z1(m), z2(m), z1(n - 1), z1(m - l)
+    k.gamma_abc_g1 = z1(l)
+    k.alpha_g1, k.beta_g1, k.delta_g1 = (np.zeros(12, np.uint64) for _ in range(3))
+    k.beta_g2, k.gamma_g2, k.delta_g2 = (np.zeros(24, np.uint64) for _ in range(3))
+    args = [nc, l, m] + [_p(x) for x in mats] + [_p(tox), _p(g1), _p(g2)]
+    for pair in (k.a_query, k.b_g1_query, k.b_g2_query, k.h_query, k.l_query):
+        args += [_p(pair[0]), _p(pair[1])]
+    args += [_p(x) for x in (k.alpha_g1, k.beta_g1, k.delta_g1, k.beta_g2, k.gamma_g2, k.delta_g2)]
+    args += [_p(k.gamma_abc_g1[0]), _p(k.gamma_abc_g1[1])]
+    st = lib().ark_cpu_groth16_setup(*args)
+    if st != 0:
+        raise ValueError("ark_cpu_groth16_setup failed (%d)" % st)
+    return k
+
+
+def constraint_evals(csr_a, csr_b, csr_c, num_constraints, num_instance, z_mont):
+    """a, b, c evaluation vectors of witness_map_from_matrices (Montgomery limbs, domain size)."""
+    nc, l = int(num_constraints), int(num_instance)
+    log_n = max(0, (nc + l - 1).bit_length())
+    n = 1 << log_n
+    mats = []
+    for rp, ci, cf in (csr_a, csr_b, csr_c):
+        mats += [_c(rp), _c(ci, np.uint32), _c(cf)]
+    z = _c(z_mont)
+    a, b, c = (np.zeros((n, 4), np.uint64) for _ in range(3))
+    lib().ark_cpu_constraint_evals(nc, l, log_n, *[_p(x) for x in mats], _p(z), _p(a), _p(b), _p(c))
+    return a, b, c
+
+
+def proving_key_of(k):
+    return CpuProvingKey(k.num_variables, k.num_instance, k.domain_size, k.a_query, k.b_g1_query, k.b_g2_query,
+                         k.h_query, k.l_query, k.alpha_g1, k.beta_g1, k.delta_g1, k.beta_g2, k.delta_g2)

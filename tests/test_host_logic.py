@@ -213,3 +213,32 @@ def test_domain_too_large_maps_to_polynomial_degree_too_large(b2z):
     with pytest.raises(b2z.PolynomialDegreeTooLarge):
         b2z.Radix2EvaluationDomain(None, (1 << 32) + 1)
     assert issubclass(b2z.PolynomialDegreeTooLarge, b2z.SynthesisError)
+
+
+def test_uploaded_handles_are_bound_to_their_context_and_shard(b2z):
+    """ProvingKey.upload / ConstraintMatrices.upload never hand back a handle that was made for another
+    context or another shard (host logic only: the handle is faked, nothing touches the GPU)."""
+    import numpy as np
+    z12, z24 = np.zeros((1, 12), np.uint64), np.zeros((1, 24), np.uint64)
+    pk = b2z.ProvingKey(1, 1, 1, (z12, None), (z12, None), (z24, None), (z12[:0], None), (z12[:0], None),
+                        z12[0], z12[0], z12[0], z24[0], z24[0])
+    ctx_a, ctx_b = object(), object()
+    pk._ctx, pk._handle, pk._spec = ctx_a, object(), (0, 2, None)
+    assert pk.upload(ctx_a, rank=0, world=2) is pk
+    with pytest.raises(ValueError):
+        pk.upload(ctx_b, rank=0, world=2)
+    with pytest.raises(ValueError):
+        pk.upload(ctx_a, rank=1, world=2)
+    with pytest.raises(ValueError):
+        pk.upload(ctx_a)
+    with pytest.raises(ValueError):
+        b2z.Groth16.create_proof_partial(ctx_b, pk, None, None, None, None, 1, 1)
+    rp = np.zeros(1, np.uint64)
+    cm = b2z.ConstraintMatrices(1, 0, 0, (rp, np.zeros(0, np.uint32), np.zeros((0, 4), np.uint64)),
+                                (rp, np.zeros(0, np.uint32), np.zeros((0, 4), np.uint64)),
+                                (rp, np.zeros(0, np.uint32), np.zeros((0, 4), np.uint64)))
+    cm._ctx, cm._handle = ctx_a, object()
+    assert cm.upload(ctx_a) is cm
+    with pytest.raises(ValueError):
+        cm.upload(ctx_b)
+    pk._handle = cm._handle = None          # nothing real to free

@@ -72,3 +72,42 @@ def test_prove_bytes_match_python_oracle(cpu_oracle, b2z, codec, circuits, golde
     cpu_oracle.set_threads(1)
     assert cpk.prove(a, b, c, codec.fr_to_mont_limbs(inst.z), rs[0], rs[1]) == got
     cpu_oracle.set_threads(4)
+
+
+def _key_equal(codec, key, opk):
+    """CpuKey / product ProvingKey arrays == Python-oracle key, element by element."""
+    g1 = lambda pair: codec.g1_from_limbs(pair[0], pair[1])
+    g2 = lambda pair: codec.g2_from_limbs(pair[0], pair[1])
+    assert g1(key.a_query) == opk.a_query
+    assert g1(key.b_g1_query) == opk.b_g1_query
+    assert g2(key.b_g2_query) == opk.b_g2_query
+    assert g1(key.h_query) == opk.h_query
+    assert g1(key.l_query) == opk.l_query
+    one1 = lambda x: codec.g1_from_limbs(x.reshape(1, -1))[0]
+    one2 = lambda x: codec.g2_from_limbs(x.reshape(1, -1))[0]
+    assert (one1(key.alpha_g1), one1(key.beta_g1), one1(key.delta_g1)) == (opk.alpha_g1, opk.beta_g1, opk.delta_g1)
+    assert (one2(key.beta_g2), one2(key.delta_g2)) == (opk.beta_g2, opk.delta_g2)
+
+
+@pytest.mark.parametrize("which", ["fibonacci", "matrix2"])
+def test_cpu_setup_matches_python_oracle(cpu_oracle, b2z, codec, circuits, which):
+    """ark_cpu_groth16_setup (the reference arm's key generation) == OG.setup on the same toxic waste."""
+    inst = circuits.fibonacci_circuit(0, 1, 10) if which == "fibonacci" else \
+        circuits.matrix_circuit([[1, 2], [3, 4]], [[4, 3], [2, 1]])
+    r1 = oracle_r1cs(inst)
+    toxic = [random.Random(7).randrange(1, O.R_MOD) for _ in range(5)]
+    opk = OG.setup(r1, toxic=toxic)
+    cm = b2z.ConstraintMatrices.from_rows(inst.num_instance, inst.num_witness, inst.a, inst.b, inst.c)
+    key = cpu_oracle.groth16_setup(cm.a, cm.b, cm.c, cm.num_constraints, cm.num_instance_variables, cm.num_variables,
+                                   toxic)
+    _key_equal(codec, key, opk)
+    assert codec.g2_from_limbs(key.gamma_g2.reshape(1, -1))[0] == opk.gamma_g2
+    assert codec.g1_from_limbs(*key.gamma_abc_g1) == opk.gamma_abc_g1
+    # the row evaluation of the same library == the oracle's, and the proof from this key verifies
+    z = codec.fr_to_mont_limbs(inst.z)
+    a, b, c = cpu_oracle.constraint_evals(cm.a, cm.b, cm.c, cm.num_constraints, cm.num_instance_variables, z)
+    ea, eb, ec = OG.constraint_evaluations(r1, inst.z)
+    assert [codec.fr_from_mont_limbs(x) for x in (a, b, c)] == [ea, eb, ec]
+    rs = codec.fr_to_mont_limbs([5, 9])
+    proof = cpu_oracle.proving_key_of(key).prove(a, b, c, z, rs[0], rs[1])
+    assert proof == OG.prove(opk, r1, inst.z, 5, 9)[1]

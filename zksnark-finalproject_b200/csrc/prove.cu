@@ -76,6 +76,10 @@ FrEl fr_load_host(const uint64_t v[4]) {
 // Proving key
 // ---------------------------------------------------------------------------
 struct PkImpl {
+  // A key handle holds per-proof scratch (below), so it belongs to exactly ONE context: the one it was
+  // uploaded through.  Every entry point checks this and returns B2Z_EINVAL for a foreign context.
+  const Ctx* owner = nullptr;
+  bool* assignment_flag = nullptr;   // b2z_groth16_shard_begin .. shard_finish window (r1cs.cu)
   uint32_t log_n = 0;
   uint64_t m = 0, l = 0;
   // shard: variables [lo, lo+ma) of the a/b queries, [l_lo, l_lo+ml) of the witness part, bit-reversed
@@ -143,6 +147,11 @@ void msm_entry(Ctx& c, const uint64_t* bases, const uint8_t* inf_bitmap, const u
   B2Z_REQUIRE(out_xyz != nullptr, B2Z_EINVAL, "msm: out is NULL");
   B2Z_REQUIRE(n == 0 || (bases != nullptr && scalars != nullptr), B2Z_EINVAL, "msm: NULL input");
   B2Z_REQUIRE(n < (1ull << 28), B2Z_ESIZE, "msm: more than 2^28 points in one call");
+  // The signed-window recoding covers 255 bits (Fr::MODULUS_BIT_SIZE, what msm_bigint itself assumes): a scalar with
+  // bit 255 set would index past the bucket array.  into_bigint() of an Fr element never has it; reject anything else.
+  for (uint64_t i = 0; i < n; i++)
+    B2Z_REQUIRE((scalars[4 * i + 3] >> 63) == 0, B2Z_EINVAL,
+                "msm: scalar >= 2^255 (scalars must be canonical Fr bigints, i.e. into_bigint())");
   cudaStream_t st = c.stream;
   // identity as arkworks represents it: (1, 1, 0), Montgomery limbs
   std::memset(out_xyz, 0, 3 * kLimbs * 8);
@@ -369,22 +378,36 @@ struct b2z_pk {
 };
 
 namespace b2z {
+// the key's scratch is per-proof state: only the context that uploaded it may prove on it
+PkImpl& pk_of(Ctx& c, const b2z_pk* pk, const char* who) {
+  if (pk == nullptr) throw StatusError{B2Z_EINVAL, std::string(who) + ": key is NULL"};
+  PkImpl& P = const_cast<b2z_pk*>(pk)->impl;
+  if (P.owner != &c)
+    throw StatusError{B2Z_EINVAL, std::string(who) + ": this b2z_pk was uploaded through another b2z_ctx (a key handle "
+                                                     "belongs to one context; upload one copy per context)"};
+  return P;
+}
 bool pk_matches(const b2z_pk* pk, uint32_t log_n, uint64_t m, uint64_t l) {
   return pk->impl.log_n == log_n && pk->impl.m == m && pk->impl.l == l;
 }
 void prove_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
                              const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]) {
-  prove_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, proof_out);
+  prove_device(c, pk_of(c, pk, "b2z_groth16_prove"), d_a, d_b, d_c, d_z, r, s, proof_out);
 }
 void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, const FrEl* d_z,
                                      const uint64_t r[4], const uint64_t s[4], uint8_t* partial_out) {
-  prove_partial_device(c, const_cast<b2z_pk*>(pk)->impl, d_a, d_b, d_c, d_z, r, s, partial_out);
+  prove_partial_device(c, pk_of(c, pk, "b2z_groth16_prove_partial"), d_a, d_b, d_c, d_z, r, s, partial_out);
 }
 void prove_begin_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
-  prove_begin(c, const_cast<b2z_pk*>(pk)->impl, d_z, r, s);
+  prove_begin(c, pk_of(c, pk, "b2z_groth16_shard_begin"), d_z, r, s);
 }
+void pk_bind_assignment_flag(const b2z_pk* pk, bool* flag) { const_cast<b2z_pk*>(pk)->impl.assignment_flag = flag; }
 void prove_finish_on(Ctx& c, const b2z_pk* pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, uint8_t* partial_out) {
-  PkImpl& P = const_cast<b2z_pk*>(pk)->impl;
+  PkImpl& P = pk_of(c, pk, "b2z_groth16_shard_finish");
+  if (P.assignment_flag != nullptr) {
+    *P.assignment_flag = false;
+    P.assignment_flag = nullptr;
+  }
   prove_quotient(c, P, d_a, d_b, d_c);
   prove_end(c, P, partial_out);
 }
@@ -429,6 +452,7 @@ b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from
                 B2Z_EINVAL, "b2z_pk_upload: NULL query array");
     std::unique_ptr<b2z_pk> pk(new b2z_pk());
     PkImpl& P = pk->impl;
+    P.owner = &c;
     P.log_n = d->log_domain;
     P.m = m;
     P.l = l;
@@ -547,7 +571,7 @@ b2z_status b2z_groth16_prove_partial(b2z_ctx* ctx, const b2z_pk* pk_c, const uin
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk_c && a_evals && b_evals && c_evals && z && r && s && partial_out, B2Z_EINVAL,
                 "b2z_groth16_prove_partial: NULL argument");
-    PkImpl& P = const_cast<b2z_pk*>(pk_c)->impl;
+    PkImpl& P = pk_of(c, pk_c, "b2z_groth16_prove_partial");
     const size_t n = (size_t)1 << P.log_n;
     B2Z_CUDA(cudaMemcpyAsync(P.z.p, z, P.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
     B2Z_CUDA(cudaMemcpyAsync(P.ea.p, a_evals, n * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
@@ -581,7 +605,7 @@ b2z_status b2z_groth16_prove(b2z_ctx* ctx, const b2z_pk* pk_c, const uint64_t* a
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk_c && a_evals && b_evals && c_evals && z && r && s && proof_out, B2Z_EINVAL,
                 "b2z_groth16_prove: NULL argument");
-    PkImpl& P = const_cast<b2z_pk*>(pk_c)->impl;
+    PkImpl& P = pk_of(c, pk_c, "b2z_groth16_prove");
     const size_t n = (size_t)1 << P.log_n;
     B2Z_CUDA(cudaMemcpyAsync(P.z.p, z, P.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
     B2Z_CUDA(cudaMemcpyAsync(P.ea.p, a_evals, n * sizeof(FrEl), cudaMemcpyHostToDevice, c.stream));
@@ -597,9 +621,13 @@ b2z_status b2z_groth16_prove_device(b2z_ctx* ctx, const b2z_pk* pk_c, uint64_t* 
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk_c && d_a && d_b && d_c && d_z && r && s && proof_out, B2Z_EINVAL,
                 "b2z_groth16_prove_device: NULL argument");
-    PkImpl& P = const_cast<b2z_pk*>(pk_c)->impl;
-    // the caller's buffers were produced on some other stream: order after everything issued so far
-    B2Z_CUDA(cudaDeviceSynchronize());
+    PkImpl& P = pk_of(c, pk_c, "b2z_groth16_prove_device");
+    // The caller's buffers must be complete, or produced on the legacy default stream (what a torch / plain-CUDA
+    // caller uses): the library's non-blocking streams are ordered after it by an event -- no device-wide
+    // synchronisation, which would serialise every context that shares this GPU.
+    B2Z_CUDA(cudaEventRecord(P.ev_z, cudaStreamLegacy));
+    B2Z_CUDA(cudaStreamWaitEvent(c.stream, P.ev_z, 0));
+    B2Z_CUDA(cudaStreamWaitEvent(c.aux[0], P.ev_z, 0));
     prove_device(c, P, reinterpret_cast<FrEl*>(d_a), reinterpret_cast<FrEl*>(d_b), reinterpret_cast<FrEl*>(d_c),
                  reinterpret_cast<const FrEl*>(d_z), r, s, proof_out);
   });

@@ -19,6 +19,7 @@ struct CsrDev {
 };
 
 struct R1csImpl {
+  const Ctx* owner = nullptr;      // holds per-proof scratch (z, ea, eb, ec): belongs to the uploading context
   uint64_t nc = 0, l = 0, m = 0;
   uint32_t log_n = 0;
   CsrDev mat[3];
@@ -137,6 +138,18 @@ struct b2z_r1cs {
   R1csImpl impl;
 };
 
+namespace b2z {
+namespace {
+R1csImpl& r1cs_of(Ctx& c, b2z_r1cs* r, const char* who) {
+  if (r == nullptr) throw StatusError{B2Z_EINVAL, std::string(who) + ": r1cs is NULL"};
+  if (r->impl.owner != &c)
+    throw StatusError{B2Z_EINVAL, std::string(who) + ": this b2z_r1cs was uploaded through another b2z_ctx (a handle "
+                                                     "belongs to one context; upload one copy per context)"};
+  return r->impl;
+}
+}  // namespace
+}  // namespace b2z
+
 extern "C" {
 
 b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_instance, uint64_t num_variables,
@@ -153,6 +166,7 @@ b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_
     B2Z_REQUIRE(log_n <= 28, B2Z_ENOMEM, "b2z_r1cs_upload: domain does not fit this build's single-GPU plan");
     std::unique_ptr<b2z_r1cs> r(new b2z_r1cs());
     R1csImpl& R = r->impl;
+    R.owner = &c;
     R.nc = num_constraints; R.l = num_instance; R.m = num_variables; R.log_n = log_n;
     upload_csr(R.mat[0], a_row_ptr, a_cols, a_coeffs, num_constraints, num_variables, c.stream);
     upload_csr(R.mat[1], b_row_ptr, b_cols, b_coeffs, num_constraints, num_variables, c.stream);
@@ -178,7 +192,7 @@ b2z_status b2z_r1cs_eval(b2z_ctx* ctx, b2z_r1cs* r, const uint64_t* z, uint64_t*
                          uint64_t* c_out) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(r && z && a_out && b_out && c_out, B2Z_EINVAL, "b2z_r1cs_eval: NULL argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_r1cs_eval");
     const size_t n = (size_t)1 << R.log_n;
     cudaStream_t st = c.stream;
     B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, st));
@@ -212,7 +226,7 @@ b2z_status b2z_spmv_fr(b2z_ctx* ctx, uint64_t nrows, uint64_t ncols, const uint6
 b2z_status b2z_witness_map_from_matrices(b2z_ctx* ctx, b2z_r1cs* r, const uint64_t* z, uint64_t* h_out) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(r && z && h_out, B2Z_EINVAL, "b2z_witness_map_from_matrices: NULL argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_witness_map_from_matrices");
     const size_t n = (size_t)1 << R.log_n;
     cudaStream_t st = c.stream;
     B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, st));
@@ -227,18 +241,15 @@ b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, c
                                   const uint64_t ss[4], uint8_t proof_out[192]) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk && r && z && rr && ss && proof_out, B2Z_EINVAL, "b2z_groth16_prove_r1cs: NULL argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_groth16_prove_r1cs");
     B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_prove_r1cs: key and matrices disagree");
     // z goes up once, on the stream that prepares the MSM scalars; the row evaluation reads it on the
-    // main stream after an event
-    cudaEvent_t ev;
-    B2Z_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
-    B2Z_CUDA(cudaEventRecord(ev, c.aux[0]));
-    B2Z_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+    // main stream after an event.  cudaMemcpyDefault: z may also be a DEVICE pointer (assignment already resident).
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyDefault, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
+    B2Z_CUDA(cudaStreamWaitEvent(c.stream, R.ev_z, 0));
     eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, c.stream);
     prove_on_device_buffers(c, pk, R.ea.p, R.eb.p, R.ec.p, R.z.p, rr, ss, proof_out);
-    cudaEventDestroy(ev);
   });
 }
 
@@ -246,16 +257,13 @@ b2z_status b2z_groth16_prove_partial_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
                                           const uint64_t rr[4], const uint64_t ss[4], uint8_t* partial_out) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk && r && z && rr && ss && partial_out, B2Z_EINVAL, "b2z_groth16_prove_partial_r1cs: NULL argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_groth16_prove_partial_r1cs");
     B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_prove_partial_r1cs: key and matrices disagree");
-    cudaEvent_t ev;
-    B2Z_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
-    B2Z_CUDA(cudaEventRecord(ev, c.aux[0]));
-    B2Z_CUDA(cudaStreamWaitEvent(c.stream, ev, 0));
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyDefault, c.aux[0]));
+    B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
+    B2Z_CUDA(cudaStreamWaitEvent(c.stream, R.ev_z, 0));
     eval_rows(c, R, R.z.p, R.ea.p, R.eb.p, R.ec.p, c.stream);
     prove_partial_on_device_buffers(c, pk, R.ea.p, R.eb.p, R.ec.p, R.z.p, rr, ss, partial_out);
-    cudaEventDestroy(ev);
   });
 }
 
@@ -265,7 +273,7 @@ namespace {
 // z == NULL: reuse the one uploaded by the previous shard call on this r1cs
 void shard_assignment(Ctx& c, R1csImpl& R, const uint64_t* z, const char* who) {
   if (z != nullptr) {
-    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyHostToDevice, c.aux[0]));
+    B2Z_CUDA(cudaMemcpyAsync(R.z.p, z, R.m * sizeof(FrEl), cudaMemcpyDefault, c.aux[0]));
     B2Z_CUDA(cudaEventRecord(R.ev_z, c.aux[0]));
     R.z_valid = true;
   }
@@ -277,18 +285,21 @@ b2z_status b2z_groth16_shard_begin(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, 
                                    const uint64_t ss[4]) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(pk && r && rr && ss, B2Z_EINVAL, "b2z_groth16_shard_begin: NULL argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_groth16_shard_begin");
     B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_groth16_shard_begin: key and matrices disagree");
     shard_assignment(c, R, z, "b2z_groth16_shard_begin");
     B2Z_CUDA(cudaStreamWaitEvent(c.aux[0], R.ev_z, 0));
     prove_begin_on(c, pk, R.z.p, rr, ss);
+    // the uploaded assignment is valid for THIS proof only: shard_finish clears the flag, so a later call with
+    // z == NULL outside a begin/finish window fails instead of silently proving a stale assignment
+    pk_bind_assignment_flag(pk, &R.z_valid);
   });
 }
 
 b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r, uint32_t which, const uint64_t* z, uint64_t* d_out) {
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(r && d_out && which < 3, B2Z_EINVAL, "b2z_r1cs_coset_evals: bad argument");
-    R1csImpl& R = r->impl;
+    R1csImpl& R = r1cs_of(c, r, "b2z_r1cs_coset_evals");
     shard_assignment(c, R, z, "b2z_r1cs_coset_evals");
     cudaStream_t st = c.stream;
     B2Z_CUDA(cudaStreamWaitEvent(st, R.ev_z, 0));

@@ -201,6 +201,8 @@ class ConstraintMatrices:
 
     def upload(self, ctx):
         if self._handle is not None:
+            if ctx is not self._ctx:
+                raise ValueError("ConstraintMatrices already uploaded through another context; call free() first")
             return self
         h = ctypes.c_void_p()
         args = []
@@ -348,12 +350,19 @@ class ProvingKey:
         self.beta_g2, self.delta_g2 = beta_g2, delta_g2
         self._ctx = None
         self._handle = None
+        self._spec = None
 
     def upload(self, ctx, rank=0, world=1, weights=None):
         """b2z_pk_upload / b2z_pk_upload_shard: copies the key (or this rank's point shard of
         it) to the device, once per circuit.  weights (one positive integer per rank): uneven
         shards through b2z_pk_upload_slice -- rank k gets weights[k] / sum(weights) of the points."""
+        spec = (int(rank), int(world), tuple(int(w) for w in weights) if weights is not None else None)
         if self._handle is not None:
+            # a handle holds per-proof scratch and belongs to ONE context and ONE shard: never hand back a
+            # handle that does not match what the caller asked for (free() first to re-upload)
+            if ctx is not self._ctx or spec != self._spec:
+                raise ValueError("ProvingKey already uploaded through another context or as another shard "
+                                 "(%r); call free() before uploading it again" % (self._spec,))
             return self
         keep = []
 
@@ -387,7 +396,7 @@ class ProvingKey:
                                                    int(den), ctypes.byref(h)))
         else:
             ctx.check(ctx._lib.b2z_pk_upload_shard(ctx.handle, ctypes.byref(d), int(rank), int(world), ctypes.byref(h)))
-        self._ctx, self._handle = ctx, h
+        self._ctx, self._handle, self._spec = ctx, h, spec
         self.shard = (int(rank), int(world))
         return self
 
@@ -544,6 +553,9 @@ class Groth16:
     def create_proof_partial(ctx, pk, a, b, c, full_assignment, r, s):
         """This rank's share of a point-sharded proof (pk uploaded with upload(ctx, rank, world)):
         B2Z_PARTIAL_BYTES of XYZZ partial sums.  Every rank passes the same full inputs."""
+        if pk._handle is None or pk._ctx is not ctx:
+            raise ValueError("create_proof_partial: upload the key as a shard through this context first "
+                             "(pk.upload(ctx, rank, world))")
         a, b, c, z = _fr_array(a), _fr_array(b), _fr_array(c), _fr_array(full_assignment)
         if a.shape[0] != pk.domain_size or z.shape[0] != pk.num_variables:
             raise ValueError("inputs do not match the key")
@@ -556,6 +568,8 @@ class Groth16:
     @staticmethod
     def create_proof_partial_with_matrices(ctx, pk, cm, full_assignment, r, s):
         """create_proof_partial with the constraint rows evaluated on the GPU (only z crosses PCIe)."""
+        if pk._handle is None or pk._ctx is not ctx:
+            raise ValueError("create_proof_partial_with_matrices: upload the key as a shard through this context first")
         cm.upload(ctx)
         z = _fr_array(full_assignment)
         rs = codec.fr_to_mont_limbs([r, s])
