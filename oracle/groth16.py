@@ -263,10 +263,11 @@ class ProvingKey:
     pass
 
 
-def setup(r1cs, seed=0xB2000004, toxic=None):
-    """generate_random_parameters_with_reduction semantics with the standard
-    generators (the oracle's own toxic waste; pk layouts match ark-groth16's
-    ProvingKey so the keys are interchangeable)."""
+def setup(r1cs, seed=0xB2000004, toxic=None, g1_gen=None, g2_gen=None):
+    """generate_parameters_with_qap semantics; by default with the standard
+    generators and the oracle's own toxic waste (pk layouts match ark-groth16's
+    ProvingKey so the keys are interchangeable).  g1_gen / g2_gen: the random
+    generators Groth16::setup draws (oracle/ark_rng.py setup_draws)."""
     rnd = random.Random(seed)
     if toxic is None:
         toxic = [rnd.randrange(1, R_MOD) for _ in range(5)]
@@ -291,8 +292,8 @@ def setup(r1cs, seed=0xB2000004, toxic=None):
     zt = dom.evaluate_vanishing_polynomial(tau)
     ginv = pow(gamma, -1, R_MOD)
     dinv = pow(delta, -1, R_MOD)
-    fb1 = FixedBase(G1, G1_GEN)
-    fb2 = FixedBase(G2, G2_GEN)
+    fb1 = FixedBase(G1, G1_GEN if g1_gen is None else g1_gen)
+    fb2 = FixedBase(G2, G2_GEN if g2_gen is None else g2_gen)
     pk = ProvingKey()
     pk.domain_size, pk.num_instance, pk.num_variables = n, l, m
     pk.a_query = fb1.mul_many(At)

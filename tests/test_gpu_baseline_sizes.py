@@ -271,3 +271,24 @@ def test_key_and_matrices_belong_to_their_context(b2z, ctx, codec):
     assert b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, 3, 4) == want
     cm.free()
     pk.free()
+
+
+def test_fibonacci_route_seed_42_on_the_gpu(b2z, ctx, codec, circuits):
+    """fibbonaci_handler.rs:99-110 from the seed: key with the RANDOM generators Groth16::setup draws, r and s from
+    the same stream; the GPU proof equals the committed fixture (tests/golden/fibonacci_seed42.json)."""
+    import json
+    from oracle import ark_rng as A, groth16 as OG
+    from helpers import oracle_r1cs, pk_limbs
+    with open(os.path.join(os.path.dirname(__file__), "golden", "fibonacci_seed42.json")) as f:
+        case = json.load(f)
+    inst = circuits.fibonacci_circuit(case["a"], case["b"], case["num_of_rounds"])
+    r1 = oracle_r1cs(inst)
+    rng = A.StdRng.seed_from_u64(case["seed"])
+    d = A.setup_draws(rng, 16)
+    r, s = A.prove_draws(rng)
+    opk = OG.setup(r1, toxic=[d["alpha"], d["beta"], d["gamma"], d["delta"], d["tau"]], g1_gen=d["g1"], g2_gen=d["g2"])
+    pk = b2z.ProvingKey(*pk_limbs(codec, opk))
+    got = b2z.Groth16.create_random_proof_with_reduction(ctx, pk, inst.matrices, inst.num_constraints, inst.z,
+                                                         iter([r, s]).__next__)
+    assert got.hex() == case["proof"]
+    pk.free()
