@@ -201,6 +201,33 @@ B2Z_API b2z_status b2z_fixed_base_mul_g1(b2z_ctx* ctx, const uint64_t* scalars, 
 B2Z_API b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t n,
                                          uint64_t* out_points, uint8_t* out_inf);
 
+/* ---- ark_groth16 verifier over the reference's wire formats (host only: no GPU, no ctx) -----------------
+ * b2z_groth16_prepare_verifying_key = ark_groth16::prepare_verifying_key followed by
+ * PreparedVerifyingKey::serialize_compressed -- the bytes encode_pvk base64-encodes
+ * (src/arkworks/matrix_proof_of_work/io.rs:62-68; built at src/arkworks/backend/matrix_proof.rs:134-136):
+ *   vk (alpha_g1 48 | beta_g2 96 | gamma_g2 96 | delta_g2 96 | u64 count | count x 48 gamma_abc_g1)
+ *   | alpha_g1_beta_g2 (Fq12, 12 x 48 B little-endian) | gamma_g2_neg_pc | delta_g2_neg_pc
+ *   (G2Prepared: u64 count | count x 3 x 96 B line coefficients | 1 B infinity flag).
+ * Call with pvk_out == NULL to get the size in *pvk_len (40 106 + 48 num_instance bytes).
+ * b2z_groth16_verify_with_processed_vk = Groth16::verify_with_processed_vk (matrix_proof.rs:199-206) on
+ * those bytes, the 192 proof bytes and the public inputs (Fr Montgomery limbs, WITHOUT the leading 1):
+ * *valid = 1 / 0; B2Z_EINVAL for malformed encodings or a wrong input count
+ * (SynthesisError::MalformedVerifyingKey / a deserialization error in arkworks).                         */
+typedef struct b2z_vk_desc {
+  uint64_t num_instance;         /* length of gamma_abc_g1 (public inputs + 1)          */
+  const uint64_t* alpha_g1;      /* 12 limbs                                            */
+  const uint64_t* beta_g2;       /* 24 limbs                                            */
+  const uint64_t* gamma_g2;
+  const uint64_t* delta_g2;
+  const uint64_t* gamma_abc_g1;  /* num_instance x 12 limbs                             */
+  const uint8_t* gamma_abc_inf;  /* identity bitmap or NULL                             */
+} b2z_vk_desc;
+B2Z_API b2z_status b2z_groth16_prepare_verifying_key(const b2z_vk_desc* vk, uint8_t* pvk_out, uint64_t capacity,
+                                                     uint64_t* pvk_len);
+B2Z_API b2z_status b2z_groth16_verify_with_processed_vk(const uint8_t* pvk, uint64_t pvk_len,
+                                                        const uint64_t* public_inputs, uint64_t num_inputs,
+                                                        const uint8_t proof[192], int32_t* valid);
+
 /* ---- measurement hooks ----------------------------------------------------------------
  * Phase timers use CUDA events recorded on the stream each kernel is launched on.
  * Phases (index into the arrays of b2z_profile_read, length B2Z_PHASE_COUNT):

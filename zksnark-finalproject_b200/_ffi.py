@@ -27,6 +27,11 @@ class PkDesc(ctypes.Structure):
     ]
 
 
+class VkDesc(ctypes.Structure):
+    _fields_ = [("num_instance", ctypes.c_uint64), ("alpha_g1", vp), ("beta_g2", vp), ("gamma_g2", vp),
+                ("delta_g2", vp), ("gamma_abc_g1", vp), ("gamma_abc_inf", vp)]
+
+
 # name -> (restype, argtypes); the test-suite checks this table against include/b200zk.h
 SIGNATURES = {
     "b2z_ctx_create": (ctypes.c_int32, [ctypes.c_int, ctypes.POINTER(vp)]),
@@ -63,6 +68,10 @@ SIGNATURES = {
     "b2z_groth16_shard_begin": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp]),
     "b2z_r1cs_coset_evals": (ctypes.c_int32, [vp, vp, ctypes.c_uint32, vp, vp]),
     "b2z_groth16_shard_finish": (ctypes.c_int32, [vp, vp, vp, vp, vp, vp]),
+    "b2z_groth16_prepare_verifying_key": (ctypes.c_int32, [ctypes.POINTER(VkDesc), vp, ctypes.c_uint64,
+                                                            ctypes.POINTER(ctypes.c_uint64)]),
+    "b2z_groth16_verify_with_processed_vk": (ctypes.c_int32, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp,
+                                                               ctypes.POINTER(ctypes.c_int32)]),
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),

@@ -399,6 +399,45 @@ inline bool final_exponentiation(const Fq12& f, Fq12* out) {
   return true;
 }
 
+// Fr element (Montgomery limbs, R = 2^256) -> canonical integer: one Montgomery reduction of (a, 0)
+static const uint64_t kFrInv = 0xfffffffeffffffffull;   // -r^-1 mod 2^64
+inline bool fr_mont_to_canonical(const uint64_t a[4], uint64_t out[4]) {
+  for (int i = 3; i >= 0; i--) {
+    if (a[i] != kFrModulus[i]) { if (a[i] > kFrModulus[i]) return false; break; }
+    if (i == 0) return false;   // a == r
+  }
+  uint64_t t[5] = {a[0], a[1], a[2], a[3], 0};
+  for (int i = 0; i < 4; i++) {
+    const uint64_t m = t[0] * kFrInv;
+    u128 x = (u128)m * kFrModulus[0] + t[0];
+    uint64_t c = (uint64_t)(x >> 64);
+    for (int j = 1; j < 4; j++) {
+      x = (u128)m * kFrModulus[j] + t[j] + c;
+      t[j - 1] = (uint64_t)x;
+      c = (uint64_t)(x >> 64);
+    }
+    x = (u128)t[4] + c;
+    t[3] = (uint64_t)x;
+    t[4] = (uint64_t)(x >> 64);
+  }
+  bool ge = t[4] != 0;
+  if (!ge) {
+    ge = true;
+    for (int i = 3; i >= 0; i--)
+      if (t[i] != kFrModulus[i]) { ge = t[i] > kFrModulus[i]; break; }
+  }
+  if (ge) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)t[i] - kFrModulus[i] - borrow;
+      t[i] = (uint64_t)d;
+      borrow = (uint64_t)(d >> 64) & 1;
+    }
+  }
+  std::memcpy(out, t, 32);
+  return true;
+}
+
 // ------------------------------------------------------------------ PreparedVerifyingKey and its wire format
 struct PreparedVk {
   G1Aff alpha_g1;

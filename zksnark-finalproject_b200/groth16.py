@@ -413,6 +413,29 @@ class VerifyingKey:
         self.alpha_g1, self.beta_g2, self.gamma_g2, self.delta_g2 = alpha_g1, beta_g2, gamma_g2, delta_g2
         self.gamma_abc_g1 = gamma_abc_g1          # (limbs (l, 12), identity bitmap)
 
+    def prepare(self):
+        """ark_groth16::prepare_verifying_key(&vk) serialized with serialize_compressed: the bytes the reference's
+        encode_pvk base64-encodes into the `pvk` response field (matrix_proof.rs:134-136, io.rs:62-68).
+        Host-only (b2z_groth16_prepare_verifying_key): no GPU involved."""
+        L = _ffi.lib()
+        keep = [np.ascontiguousarray(x, dtype=np.uint64).reshape(-1) for x in
+                (self.alpha_g1, self.beta_g2, self.gamma_g2, self.delta_g2, self.gamma_abc_g1[0])]
+        inf = self.gamma_abc_g1[1]
+        inf = np.ascontiguousarray(inf, dtype=np.uint8) if inf is not None else None
+        d = _ffi.VkDesc()
+        d.num_instance = int(np.asarray(self.gamma_abc_g1[0]).shape[0])
+        d.alpha_g1, d.beta_g2, d.gamma_g2, d.delta_g2, d.gamma_abc_g1 = (_ptr(x) for x in keep)
+        d.gamma_abc_inf = _ptr(inf)
+        n = ctypes.c_uint64()
+        st = L.b2z_groth16_prepare_verifying_key(ctypes.byref(d), None, 0, ctypes.byref(n))
+        if st != _ffi.B2Z_OK:
+            raise _ffi.B2zError(st, "b2z_groth16_prepare_verifying_key: malformed verifying key")
+        out = np.zeros(n.value, dtype=np.uint8)
+        st = L.b2z_groth16_prepare_verifying_key(ctypes.byref(d), _ptr(out), n.value, ctypes.byref(n))
+        if st != _ffi.B2Z_OK:
+            raise _ffi.B2zError(st, "b2z_groth16_prepare_verifying_key failed")
+        return out.tobytes()
+
 
 def _batch_inverse(values):
     """Montgomery's trick over Fr (host integers)."""
@@ -681,3 +704,21 @@ class Groth16:
         return Groth16.create_proof_with_reduction(ctx, pk, a, b, c, z, r, s)
 
     prove = create_random_proof_with_reduction
+
+    @staticmethod
+    def verify_with_processed_vk(pvk_bytes, public_inputs, proof_bytes):
+        """Groth16::verify_with_processed_vk(&pvk, &public_inputs, &proof) on the wire formats the reference's
+        /verify routes receive (matrix_proof.rs:199-206): pvk = PreparedVerifyingKey::serialize_compressed bytes,
+        public_inputs = canonical ints WITHOUT the leading 1, proof = 192 bytes.  Host-only.  Raises SynthesisError
+        for malformed bytes or a wrong number of inputs (MalformedVerifyingKey), else returns True / False."""
+        pvk = np.frombuffer(bytes(pvk_bytes), dtype=np.uint8).copy()
+        proof = np.frombuffer(bytes(proof_bytes), dtype=np.uint8).copy()
+        if proof.size != 192:
+            raise SynthesisError("proof must be 192 bytes")
+        x = codec.fr_to_mont_limbs([int(v) for v in public_inputs])
+        ok = ctypes.c_int32(0)
+        st = _ffi.lib().b2z_groth16_verify_with_processed_vk(_ptr(pvk), pvk.size, _ptr(x) if len(public_inputs) else None,
+                                                             len(public_inputs), _ptr(proof), ctypes.byref(ok))
+        if st != _ffi.B2Z_OK:
+            raise SynthesisError("MalformedVerifyingKey / malformed proof or inputs (status %d)" % st)
+        return bool(ok.value)
