@@ -272,6 +272,38 @@ B2Z_API b2z_status b2z_r1cs_coset_evals(b2z_ctx* ctx, b2z_r1cs* r1cs, uint32_t w
 B2Z_API b2z_status b2z_groth16_shard_finish(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_a, const uint64_t* d_b,
                                             const uint64_t* d_c, uint8_t* partial_out);
 
+/* ---- ONE proof by 2, 4 or 8 GPUs of a box with the WITNESS MAP ITSELF tile-sharded -----------
+ * One rank per GPU (a process per GPU under torchrun, or a host thread per GPU in one process).  Every rank holds
+ * shard `rank` of the key (b2z_pk_upload_shard) and the matrices.  Per proof:
+ *   - each rank moves 1 / W of the assignment over PCIe and copies that slice into the peers' memory over NVLink;
+ *   - the witness map runs on n / W elements per rank: the transform's stages are split between a column-owned
+ *     and a row-owned layout, and each layout change (an all-to-all transpose) is fused into the STORE of the
+ *     pass before it -- the kernel writes its output tile straight into the peers' buffers over NVLink
+ *     (3 exchanges per proof, 3 x n x 32 / W bytes per rank at most);
+ *   - rank k ends with coefficients [n k / W, n (k + 1) / W) of h (bit-reversed order) = exactly the h bases of
+ *     its key shard, so the five MSM accumulations follow back to back with no further data exchange;
+ *   - the 1344-byte partial sums meet in a caller-provided SHARED HOST buffer and every rank returns the proof.
+ * The library links no communication runtime: peers are attached either by CUDA IPC handle (another process)
+ * or by plain device pointer (same process), and ranks synchronise by a host barrier on the shared buffer
+ * (b2z_dist_shared_bytes(world) bytes, zero-initialised, visible to all ranks: POSIX shared memory between
+ * processes, ordinary memory between threads).  All ranks must call b2z_dist_prove for the same proof with the
+ * same r, s; the call returns on every rank with the same 192 bytes.
+ *   z: the full assignment (host or device pointer; each rank reads only its slice), or, with
+ *      z_is_full_device_copy != 0, a device-resident full copy per rank (no exchange).
+ * B2Z_ESIZE from b2z_dist_create: the domain is too small to tile (fall back to b2z_groth16_prove_partial_r1cs). */
+typedef struct b2z_dist b2z_dist;
+B2Z_API uint64_t b2z_dist_shared_bytes(uint32_t world);
+B2Z_API b2z_status b2z_dist_create(b2z_ctx* ctx, const b2z_pk* pk_shard, b2z_r1cs* r1cs, uint32_t rank, uint32_t world,
+                                   void* shared_host, b2z_dist** out);
+B2Z_API void b2z_dist_destroy(b2z_ctx* ctx, b2z_dist* dist);
+/* this rank's exchange region: ipc_handle (64 bytes, cudaIpcMemHandle_t) and / or its device pointer */
+B2Z_API b2z_status b2z_dist_export(b2z_ctx* ctx, b2z_dist* dist, uint8_t ipc_handle[64], void** device_ptr);
+/* make rank `peer`'s region reachable: exactly one of ipc_handle (other process) / device_ptr (same process) */
+B2Z_API b2z_status b2z_dist_attach(b2z_ctx* ctx, b2z_dist* dist, uint32_t peer, const uint8_t* ipc_handle,
+                                   void* device_ptr);
+B2Z_API b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* dist, const uint64_t* z, int z_is_full_device_copy,
+                                  const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
+
 /* Page-lock caller-owned host memory (cudaHostRegister) so that the per-proof upload of the assignment runs at
  * PCIe speed instead of through the driver's staging buffer (61 MB of z at 2^22: ~1.2 ms instead of ~4 ms).  The
  * caller keeps ownership; unregister before freeing.  A Rust caller registers the Vec<Fr> it reuses per request. */

@@ -292,3 +292,96 @@ def test_fibonacci_route_seed_42_on_the_gpu(b2z, ctx, codec, circuits):
                                                          iter([r, s]).__next__)
     assert got.hex() == case["proof"]
     pk.free()
+
+
+# ------------------------------------------------------------------------------- tile-sharded prover (b2z_dist_*)
+def _dist_prove_virtual_ranks(b2z, codec, cm0, pk0, z, r, s, world, resident=False, proofs=1):
+    """`world` ranks as host threads, each with its own context / key shard / matrices on THIS GPU: the same code
+    path as one rank per GPU (peers attached by device pointer instead of IPC handle)."""
+    import threading
+    shared = np.zeros(b2z.DistributedProver.shared_bytes(world), dtype=np.uint8)
+    barrier = threading.Barrier(world)
+    exported, results, errors = [None] * world, [None] * world, []
+
+    def worker(rank):
+        try:
+            rctx = b2z.Context(0)
+            spk = b2z.ProvingKey(pk0.num_variables, pk0.num_instance, pk0.domain_size, pk0.a_query, pk0.b_g1_query,
+                                 pk0.b_g2_query, pk0.h_query, pk0.l_query, pk0.alpha_g1, pk0.beta_g1, pk0.delta_g1,
+                                 pk0.beta_g2, pk0.delta_g2)
+            rcm = b2z.ConstraintMatrices(cm0.num_instance_variables, cm0.num_witness_variables, cm0.num_constraints,
+                                         cm0.a, cm0.b, cm0.c)
+            dp = b2z.DistributedProver(rctx, spk, rcm, rank, world, shared)
+            exported[rank] = dp.export()[1]
+            barrier.wait()
+            for p in range(world):
+                if p != rank:
+                    dp.attach(p, device_ptr=exported[p])
+            barrier.wait()
+            zarg = z
+            if resident:
+                import torch
+                zt = torch.from_numpy(z.view(np.int64).copy()).cuda()
+                torch.cuda.synchronize()
+                zarg = int(zt.data_ptr())
+            results[rank] = [dp.prove(zarg, r + i, s + i, resident=resident) for i in range(proofs)]
+            barrier.wait()
+            dp.close(); spk.free(); rcm.free(); rctx.close()
+        except Exception as e:                    # surfaced below; release the others from the barrier
+            errors.append((rank, repr(e)))
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    return results
+
+
+@pytest.mark.parametrize("size,world", [(8, 2), (16, 4), (16, 8)])
+def test_tile_sharded_prover_equals_single_gpu(b2z, ctx, codec, size, world):
+    """ONE proof by `world` ranks with the witness map tile-sharded (layout changes fused into the pass stores, peers
+    written directly): every rank returns the bytes of the single-GPU proof; host z, device-resident z, several
+    proofs in a row on the same handles."""
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    ones = [[1 + (i * j) % 3 for j in range(size)] for i in range(size)]
+    cm, z_int = fast.matrix_circuit_fast(ones, ones)
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                     cm.num_variables, *_toxic(77))
+    z = codec.fr_to_mont_limbs(z_int)
+    r, s = 1234567, 7654321
+    want = [b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r + i, s + i) for i in range(2)]
+    pk.free()
+    got = _dist_prove_virtual_ranks(b2z, codec, cm, pk, z, r, s, world, proofs=2)
+    for rank in range(world):
+        assert got[rank] == want, "rank %d" % rank
+    got = _dist_prove_virtual_ranks(b2z, codec, cm, pk, z, r, s, world, resident=True)
+    assert all(g == want[:1] for g in got)
+    cm.free()
+
+
+def test_tile_sharded_prover_2p22(b2z, ctx, codec, c5):
+    """The north-star configuration (domain 2^22) through the tile-sharded prover with 8 virtual ranks."""
+    cm, z, pk, vk = c5
+    r, s = 99, 101
+    want = b2z.Groth16.create_proof_with_matrices(ctx, pk, cm, z, r, s)
+    pk.free()
+    got = _dist_prove_virtual_ranks(b2z, codec, cm, pk, z, r, s, 8)
+    assert all(g == [want] for g in got)
+
+
+def test_tile_sharded_prover_rejects_misuse(b2z, ctx, codec):
+    fast = importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+    cm, z_int = fast.matrix_circuit_fast([[1, 2], [3, 4]], [[4, 3], [2, 1]])
+    pk, _ = b2z.Groth16.generate_parameters_with_qap(ctx, cm, cm.num_constraints, cm.num_instance_variables,
+                                                     cm.num_variables, *_toxic(78))
+    shared = np.zeros(b2z.DistributedProver.shared_bytes(2), dtype=np.uint8)
+    with pytest.raises(b2z.PolynomialDegreeTooLarge):            # B2Z_ESIZE: a 2^10 domain is too small to tile
+        b2z.DistributedProver(ctx, pk, cm, 0, 2, shared)
+    pk.free()
+    with pytest.raises(b2z._ffi.B2zError):
+        b2z.DistributedProver(ctx, pk, cm, 0, 3, np.zeros(8192, dtype=np.uint8))      # world must be 2, 4 or 8
+    pk.free()
+    cm.free()

@@ -72,6 +72,12 @@ SIGNATURES = {
                                                             ctypes.POINTER(ctypes.c_uint64)]),
     "b2z_groth16_verify_with_processed_vk": (ctypes.c_int32, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp,
                                                                ctypes.POINTER(ctypes.c_int32)]),
+    "b2z_dist_shared_bytes": (ctypes.c_uint64, [ctypes.c_uint32]),
+    "b2z_dist_create": (ctypes.c_int32, [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, vp, ctypes.POINTER(vp)]),
+    "b2z_dist_destroy": (None, [vp, vp]),
+    "b2z_dist_export": (ctypes.c_int32, [vp, vp, vp, ctypes.POINTER(vp)]),
+    "b2z_dist_attach": (ctypes.c_int32, [vp, vp, ctypes.c_uint32, vp, vp]),
+    "b2z_dist_prove": (ctypes.c_int32, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),

@@ -137,6 +137,24 @@ void measure_int_peak(Ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
 void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st);
 // its two halves (the first one per input vector), for the distributed witness map of the sharded prover
 void witness_map_transform(Ctx* ctx, FrEl* x, uint32_t log_n, cudaStream_t st);
+void witness_map_transform3(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, cudaStream_t st);
+
+// Tile-sharded witness map over W = 2^wbits ranks (ntt.cu).  x / y: this rank's local vectors (a, b, c) in the
+// column-owned / row-owned layout, n / W elements each; peer_x / peer_y [vector][rank]: the same buffers of
+// every rank (peer-mapped device pointers; [..][me] = own).
+struct NttDist {
+  uint32_t wbits = 0, me = 0;
+  FrEl* x[3] = {nullptr, nullptr, nullptr};
+  FrEl* y[3] = {nullptr, nullptr, nullptr};
+  FrEl* peer_x[3][8] = {};
+  FrEl* peer_y[3][8] = {};
+};
+bool ntt_dist_supported(uint32_t log_n, uint32_t wbits);
+uint32_t ntt_dist_col_bits(uint32_t log_n, uint32_t wbits);   // position of the ownership bits of the column-owned layout
+void wm_dist_step1(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st);   // writes peers' y
+void wm_dist_step2(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st);   // reads y, writes peers' x
+void wm_dist_step3(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st);   // reads x, writes peers' y[0]
+void wm_dist_step4(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st);   // reads y[0]: h chunk, canonical
 void witness_map_quotient(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
@@ -148,7 +166,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};
   std::map<uint32_t, NttDomain> domains;
-  bool ntt_attr_set[3] = {false, false, false};
+  bool ntt_attr_set[6] = {false, false, false, false, false, false};
   bool profile = false;
   std::vector<ProfileSpan> spans;
   std::mutex span_mu;                  // spans are appended from the single calling thread; guards reads

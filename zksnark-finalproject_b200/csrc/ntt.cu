@@ -20,6 +20,8 @@
 //   * Twiddles come from per-level tables in HBM/L2 (a 32-byte load is ~100x
 //     cheaper than the 255-bit multiplication that would recompute it).
 //   * n^-1 factors are folded into the witness map's pointwise constants.
+#include <cstring>
+
 #include "common.hpp"
 
 namespace b2z {
@@ -73,19 +75,52 @@ __device__ __forceinline__ void st_fr(FrEl* p, const FrEl& v) {
   q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// Geometry of one pass: index bits [t, t+k) are transformed, C = 2^logC adjacent
+// Geometry of one pass: LOCAL index bits [t, t+k) are transformed, C = 2^logC adjacent
 // low columns ride along for coalescing (logC <= t).
 struct PassGeom {
   uint32_t t, k, logC;
 };
 
+// Everything one pass kernel needs.  Up to three vectors are transformed by one launch (blockIdx.y);
+// the witness map's a, b, c always travel together.
+//
+// Distribution (point-sharded prover, several GPUs): a rank holds n / 2^wbits elements of every vector.  Its
+// LOCAL index li is the global index gi with the wbits "ownership" bits [ob, ob + wbits) removed; those bits
+// equal the rank.  A pass never transforms an ownership bit, so the butterflies are local; only the twiddle
+// index (low bits of the GLOBAL index) and -- when the layout changes -- the store address depend on it:
+//   ob_in   position of the ownership bits of the layout the data is in (kNoDist: single GPU)
+//   ob_out  position for the layout it is stored in; the element goes to rank (gi >> ob_out) & (W - 1), at that
+//           rank's local index, through peer[vec][rank] (NVLink stores to peer memory: the all-to-all transpose
+//           between the column-owned and the row-owned layout is fused into the pass that precedes it)
+constexpr uint32_t kNoDist = 0xffu;
+constexpr int kMaxVec = 3, kMaxRanks = 8;
+enum PassFlags : uint32_t { PF_CANONICAL_OUT = 1, PF_POINTWISE_IN = 2 };
+struct PassArgs {
+  FrEl* data[kMaxVec];
+  const FrEl* tw_a;
+  const FrEl* tw_b;
+  PassGeom g;
+  uint32_t flags;
+  uint32_t ob_in, ob_out, wbits, me;
+  FrEl k1, k2;                          // PF_POINTWISE_IN: element = k1 * data[0] * data[1] - k2 * data[2]
+  FrEl* peer[kMaxVec][kMaxRanks];       // ob_out != kNoDist: output bases per vector and rank
+};
+
+__device__ __forceinline__ uint32_t insert_bits(uint32_t x, uint32_t pos, uint32_t width, uint32_t v) {
+  return ((x >> pos) << (pos + width)) | (v << pos) | (x & ((1u << pos) - 1));
+}
+__device__ __forceinline__ uint32_t remove_bits(uint32_t x, uint32_t pos, uint32_t width) {
+  return ((x >> (pos + width)) << pos) | (x & ((1u << pos) - 1));
+}
+
 // One exchange round: Q stages on local bits [p0, p0+Q) of the tile's k-bit row
 // index.  Each thread owns 8 elements: 8 >> Q groups of 2^Q.
-template <int Q, bool DIT>
-__device__ __forceinline__ void ntt_round(const Tile& tile, const FrEl* __restrict__ tw, PassGeom g, uint32_t p0,
+template <int Q, bool DIT, bool DIST>
+__device__ __forceinline__ void ntt_round(const Tile& tile, const FrEl* __restrict__ tw, const PassArgs& a, uint32_t p0,
                                           uint32_t col_base) {
   constexpr int R = 1 << Q;
   constexpr int G = 8 >> Q;
+  const PassGeom g = a.g;
   const uint32_t ngroups = (1u << (g.k + g.logC)) >> Q;
   const uint32_t cmask = (1u << g.logC) - 1;
 #pragma unroll 1
@@ -103,12 +138,15 @@ __device__ __forceinline__ void ntt_round(const Tile& tile, const FrEl* __restri
 #pragma unroll
       for (int s = 0; s < Q; s++) {
         const int r = DIT ? s : Q - 1 - s;
-        const uint32_t lvl = g.t + p0 + r;
-        const FrEl* twl = tw + ((1u << lvl) - 1);
+        const uint32_t lvl = g.t + p0 + r;                 // local bit of this stage
+        uint32_t glvl = lvl;                               // its global bit = twiddle level
+        if (DIST && lvl >= a.ob_in) glvl += a.wbits;
+        const FrEl* twl = tw + ((1u << glvl) - 1);
 #pragma unroll
         for (int e = 0; e < R; e++) {
           if (e & (1 << r)) continue;
-          const uint32_t j = ((blow | ((uint32_t)(e & ((1 << r) - 1)) << p0)) << g.t) | (col_base + c);
+          uint32_t j = ((blow | ((uint32_t)(e & ((1 << r) - 1)) << p0)) << g.t) | (col_base + c);
+          if (DIST && lvl >= a.ob_in) j = insert_bits(j, a.ob_in, a.wbits, a.me);
           const FrEl w = ldg_fr(twl + j);
           FrEl& u = x[e];
           FrEl& v = x[e | (1 << r)];
@@ -130,29 +168,30 @@ __device__ __forceinline__ void ntt_round(const Tile& tile, const FrEl* __restri
   __syncthreads();
 }
 
-template <bool DIT>
-__device__ __forceinline__ void ntt_round_q(int q, const Tile& tile, const FrEl* tw, PassGeom g, uint32_t p0,
+template <bool DIT, bool DIST>
+__device__ __forceinline__ void ntt_round_q(int q, const Tile& tile, const FrEl* tw, const PassArgs& a, uint32_t p0,
                                             uint32_t col_base) {
-  if (q == 3) ntt_round<3, DIT>(tile, tw, g, p0, col_base);
-  else if (q == 2) ntt_round<2, DIT>(tile, tw, g, p0, col_base);
-  else ntt_round<1, DIT>(tile, tw, g, p0, col_base);
+  if (q == 3) ntt_round<3, DIT, DIST>(tile, tw, a, p0, col_base);
+  else if (q == 2) ntt_round<2, DIT, DIST>(tile, tw, a, p0, col_base);
+  else ntt_round<1, DIT, DIST>(tile, tw, a, p0, col_base);
 }
 
 // All k stages of a pass on the tile in shared memory.
-template <bool DIT>
-__device__ __forceinline__ void ntt_tile_stages(const Tile& tile, const FrEl* tw, PassGeom g, uint32_t col_base) {
+template <bool DIT, bool DIST>
+__device__ __forceinline__ void ntt_tile_stages(const Tile& tile, const FrEl* tw, const PassArgs& a, uint32_t col_base) {
+  const uint32_t k = a.g.k;
   if (DIT) {
     uint32_t p0 = 0;
-    while (p0 < g.k) {
-      const int q = (g.k - p0 >= 3) ? 3 : (int)(g.k - p0);
-      ntt_round_q<true>(q, tile, tw, g, p0, col_base);
+    while (p0 < k) {
+      const int q = (k - p0 >= 3) ? 3 : (int)(k - p0);
+      ntt_round_q<true, DIST>(q, tile, tw, a, p0, col_base);
       p0 += q;
     }
   } else {
-    uint32_t top = g.k;
+    uint32_t top = k;
     while (top > 0) {
       const int q = top >= 3 ? 3 : (int)top;
-      ntt_round_q<false>(q, tile, tw, g, top - q, col_base);
+      ntt_round_q<false, DIST>(q, tile, tw, a, top - q, col_base);
       top -= q;
     }
   }
@@ -160,84 +199,134 @@ __device__ __forceinline__ void ntt_tile_stages(const Tile& tile, const FrEl* tw
 
 enum PassMode { PASS_DIF = 0, PASS_DIT = 1, PASS_DIF_DIT = 2 };
 
-// grid = n / 2^(k+logC) tiles; block = max(32, tile/8) threads;
+// grid = (n_local / 2^(k+logC) tiles, vectors); block = max(32, tile/8) threads;
 // dynamic smem = 2 * (S + S/8) * 16 bytes.
-template <int MODE>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(FrEl* __restrict__ data, const FrEl* __restrict__ tw_a,
-                                                       const FrEl* __restrict__ tw_b, PassGeom g) {
+template <int MODE, bool DIST>
+__global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ PassArgs a) {
   extern __shared__ uint4 smem[];
+  const PassGeom g = a.g;
   const uint32_t S = 1u << (g.k + g.logC);
   Tile tile{smem, smem + S + (S >> 3)};
   const uint32_t ltiles_log = g.t - g.logC;
   const uint32_t tileL = blockIdx.x & ((1u << ltiles_log) - 1);
   const uint64_t H = blockIdx.x >> ltiles_log;
   const uint32_t col_base = tileL << g.logC;
-  FrEl* base = data + ((H << (g.t + g.k)) | col_base);
+  const uint64_t base_idx = (H << (g.t + g.k)) | col_base;
+  FrEl* base = a.data[blockIdx.y] + base_idx;
   const uint32_t cmask = (1u << g.logC) - 1;
-  for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-    const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
-    tile.store(i, ld_fr(base + off));
+  if (a.flags & PF_POINTWISE_IN) {
+    const FrEl* pb = a.data[1] + base_idx;
+    const FrEl* pc = a.data[2] + base_idx;
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+      const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
+      const FrEl ab = Fr::mul(Fr::reduce(ld_fr(base + off)), ld_fr(pb + off));
+      tile.store(i, Fr::sub(Fr::mul(a.k1, ab), Fr::mul(a.k2, ld_fr(pc + off))));
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+      const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
+      tile.store(i, ld_fr(base + off));
+    }
   }
   __syncthreads();
-  if (MODE == PASS_DIF) ntt_tile_stages<false>(tile, tw_a, g, col_base);
-  if (MODE == PASS_DIT) ntt_tile_stages<true>(tile, tw_a, g, col_base);
+  if (MODE == PASS_DIF) ntt_tile_stages<false, DIST>(tile, a.tw_a, a, col_base);
+  if (MODE == PASS_DIT) ntt_tile_stages<true, DIST>(tile, a.tw_a, a, col_base);
   if (MODE == PASS_DIF_DIT) {
-    ntt_tile_stages<false>(tile, tw_a, g, col_base);
-    ntt_tile_stages<true>(tile, tw_b, g, col_base);
+    ntt_tile_stages<false, DIST>(tile, a.tw_a, a, col_base);
+    ntt_tile_stages<true, DIST>(tile, a.tw_b, a, col_base);
   }
-  for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-    const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
-    st_fr(base + off, tile.load(i));
+  const bool canon = (a.flags & PF_CANONICAL_OUT) != 0;
+  if (DIST && a.ob_out != kNoDist) {
+    // layout change fused into the store: the element's global index decides the rank and the slot
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+      const uint32_t li = (uint32_t)base_idx + (((i >> g.logC) << g.t) | (i & cmask));
+      const uint32_t gi = insert_bits(li, a.ob_in, a.wbits, a.me);
+      const uint32_t dst_rank = (gi >> a.ob_out) & ((1u << a.wbits) - 1);
+      FrEl v = tile.load(i);
+      if (canon) v = Fr::reduce(v);
+      st_fr(a.peer[blockIdx.y][dst_rank] + remove_bits(gi, a.ob_out, a.wbits), v);
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+      const uint64_t off = ((uint64_t)(i >> g.logC) << g.t) | (i & cmask);
+      FrEl v = tile.load(i);
+      if (canon) v = Fr::reduce(v);
+      st_fr(base + off, v);
+    }
   }
 }
 
-template <int MODE>
-void launch_pass(Ctx* ctx, FrEl* data, const FrEl* tw_a, const FrEl* tw_b, uint32_t log_n, PassGeom g, cudaStream_t st) {
-  const uint32_t ls = g.k + g.logC;
+template <int MODE, bool DIST>
+void launch_pass_t(Ctx* ctx, const PassArgs& a, uint32_t log_n_local, uint32_t nvec, cudaStream_t st) {
+  const uint32_t ls = a.g.k + a.g.logC;
   const uint32_t S = 1u << ls;
   const uint32_t threads = S / 8 < 32 ? 32 : S / 8;
   const size_t smem = (size_t)2 * (S + (S >> 3)) * sizeof(uint4);
   // per-device function attribute (a process may hold contexts on several GPUs): set it once per context
-  if (!ctx->ntt_attr_set[MODE]) {
-    B2Z_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const int slot = MODE * 2 + (DIST ? 1 : 0);
+  if (!ctx->ntt_attr_set[slot]) {
+    B2Z_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<MODE, DIST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   2 * ((1 << kMaxTileLog) + (1 << (kMaxTileLog - 3))) * (int)sizeof(uint4)));
-    ctx->ntt_attr_set[MODE] = true;
+    ctx->ntt_attr_set[slot] = true;
   }
-  const uint32_t grid = 1u << (log_n - ls);
-  ProfileScope ps(ctx, PH_NTT_PASS, st, (uint64_t)1 << log_n);
-  ntt_pass_kernel<MODE><<<grid, threads, smem, st>>>(data, tw_a, tw_b, g);
+  const uint32_t grid = 1u << (log_n_local - ls);
+  ProfileScope ps(ctx, PH_NTT_PASS, st, (uint64_t)nvec << log_n_local);
+  ntt_pass_kernel<MODE, DIST><<<dim3(grid, nvec), threads, smem, st>>>(a);
   B2Z_LAUNCHED(ctx);
+}
+
+template <int MODE>
+void launch_pass(Ctx* ctx, const PassArgs& a, uint32_t log_n_local, uint32_t nvec, cudaStream_t st) {
+  if (a.ob_in != kNoDist) launch_pass_t<MODE, true>(ctx, a, log_n_local, nvec, st);
+  else launch_pass_t<MODE, false>(ctx, a, log_n_local, nvec, st);
 }
 
 // Pass plan: bits [0, k0) are the contiguous low pass; the remaining high bits
 // are split into passes of at most kMaxTileLog bits, each padded with columns up
-// to the tile size.
+// to the tile size.  wbits > 0: the plan of a transform distributed over 2^wbits ranks -- the high passes run
+// on the column-owned layout (ownership bits [k0 - wbits, k0)), the low pass on the row-owned layout
+// (ownership bits [log_n - wbits, log_n)); geometries are in LOCAL bits.
 struct Plan {
   int npass = 0;
   PassGeom pass[4];   // pass[0] = low bits, ascending
+  uint32_t k0 = 0;
 };
 
-Plan make_plan(uint32_t log_n) {
+Plan make_plan(uint32_t log_n, uint32_t wbits = 0) {
   Plan p;
-  // tile = 2^ls elements per CTA: full tiles for big transforms, smaller ones for small
-  // transforms so that a 2^16..2^18 NTT still spreads over >= 256 CTAs (148 SMs)
-  uint32_t ls = log_n > 8 ? log_n - 8 : 0;
-  if (ls < 8) ls = 8;
+  const uint32_t log_local = log_n - wbits;
+  // tile = 2^ls elements per CTA (128 or 256 threads): full tiles for big transforms, smaller ones for small
+  // transforms so that a 2^16..2^18 NTT still spreads over enough CTAs (148 SMs)
+  uint32_t ls = log_local > 8 ? log_local - 8 : 0;
+  if (ls < 10) ls = 10;
   if (ls > kMaxTileLog) ls = kMaxTileLog;
   uint32_t k0 = log_n < ls ? log_n : ls;
+  if (wbits && log_n - k0 < wbits) k0 = log_n - wbits;     // the row-owned layout needs wbits high bits
+  p.k0 = k0;
   p.pass[p.npass++] = PassGeom{0, k0, 0};
-  uint32_t t = k0;
+  uint32_t t = k0 - wbits;                                  // local position of the first high bit
   uint32_t rem = log_n - k0;
   const uint32_t nhi = (rem + ls - 1) / ls;
   for (uint32_t i = 0; i < nhi; i++) {
     const uint32_t k = (rem + (nhi - i) - 1) / (nhi - i);   // balanced split
-    uint32_t logC = ls - k;
+    uint32_t logC = ls > k ? ls - k : 0;
     if (logC > t) logC = t;
+    if (wbits && logC > k0 - wbits) logC = k0 - wbits;      // columns are bits below the ownership bits
     p.pass[p.npass++] = PassGeom{t, k, logC};
     t += k;
     rem -= k;
   }
   return p;
+}
+
+PassArgs pass_args(FrEl* v0, FrEl* v1, FrEl* v2, const FrEl* tw_a, const FrEl* tw_b, PassGeom g) {
+  PassArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.data[0] = v0; a.data[1] = v1; a.data[2] = v2;
+  a.tw_a = tw_a; a.tw_b = tw_b;
+  a.g = g;
+  a.ob_in = kNoDist; a.ob_out = kNoDist;
+  return a;
 }
 
 __global__ void bitrev_kernel(FrEl* data, uint32_t log_n, FrEl scale, int has_scale, const FrEl* __restrict__ pw_lo,
@@ -324,21 +413,31 @@ FrEl fr_const(uint32_t (*f)(int)) {
 void ntt_dif(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
   if (log_n == 0) return;
   const Plan p = make_plan(log_n);
-  for (int i = p.npass - 1; i >= 0; i--) launch_pass<PASS_DIF>(ctx, data, tw, nullptr, log_n, p.pass[i], st);
+  for (int i = p.npass - 1; i >= 0; i--)
+    launch_pass<PASS_DIF>(ctx, pass_args(data, nullptr, nullptr, tw, nullptr, p.pass[i]), log_n, 1, st);
 }
 
 void ntt_dit(Ctx* ctx, const FrEl* tw, FrEl* data, uint32_t log_n, cudaStream_t st) {
   if (log_n == 0) return;
   const Plan p = make_plan(log_n);
-  for (int i = 0; i < p.npass; i++) launch_pass<PASS_DIT>(ctx, data, tw, nullptr, log_n, p.pass[i], st);
+  for (int i = 0; i < p.npass; i++)
+    launch_pass<PASS_DIT>(ctx, pass_args(data, nullptr, nullptr, tw, nullptr, p.pass[i]), log_n, 1, st);
+}
+
+// DIF with tw_a then DIT with tw_b on up to three vectors at once (natural -> natural), low stages fused
+static void ntt_dif_dit_n(Ctx* ctx, const FrEl* tw_a, const FrEl* tw_b, FrEl* v0, FrEl* v1, FrEl* v2, uint32_t nvec,
+                          uint32_t log_n, cudaStream_t st) {
+  if (log_n == 0) return;
+  const Plan p = make_plan(log_n);
+  for (int i = p.npass - 1; i >= 1; i--)
+    launch_pass<PASS_DIF>(ctx, pass_args(v0, v1, v2, tw_a, nullptr, p.pass[i]), log_n, nvec, st);
+  launch_pass<PASS_DIF_DIT>(ctx, pass_args(v0, v1, v2, tw_a, tw_b, p.pass[0]), log_n, nvec, st);
+  for (int i = 1; i < p.npass; i++)
+    launch_pass<PASS_DIT>(ctx, pass_args(v0, v1, v2, tw_b, nullptr, p.pass[i]), log_n, nvec, st);
 }
 
 void ntt_dif_dit(Ctx* ctx, const FrEl* tw_a, const FrEl* tw_b, FrEl* data, uint32_t log_n, cudaStream_t st) {
-  if (log_n == 0) return;
-  const Plan p = make_plan(log_n);
-  for (int i = p.npass - 1; i >= 1; i--) launch_pass<PASS_DIF>(ctx, data, tw_a, nullptr, log_n, p.pass[i], st);
-  launch_pass<PASS_DIF_DIT>(ctx, data, tw_a, tw_b, log_n, p.pass[0], st);
-  for (int i = 1; i < p.npass; i++) launch_pass<PASS_DIT>(ctx, data, tw_b, nullptr, log_n, p.pass[i], st);
+  ntt_dif_dit_n(ctx, tw_a, tw_b, data, nullptr, nullptr, 1, log_n, st);
 }
 
 void ntt_bitrev(Ctx* ctx, FrEl* data, uint32_t log_n, const FrEl* scale, const FrEl* pw_lo, const FrEl* pw_hi,
@@ -437,23 +536,115 @@ void witness_map_transform(Ctx* ctx, FrEl* x, uint32_t log_n, cudaStream_t st) {
   const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
   ntt_dif_dit(ctx, tw_inv, tw_cf, x, log_n, st);
 }
+// the three input vectors in the same launches (3 launches at 2^17..2^22 instead of 9)
+void witness_map_transform3(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, cudaStream_t st) {
+  const FrEl* tw_inv = ntt_twiddles(ctx, log_n, TW_INV, st);
+  const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
+  ntt_dif_dit_n(ctx, tw_inv, tw_cf, a, b, c, 3, log_n, st);
+}
 
-// a <- coefficients of (a b - c) / Z_H from the three coset evaluation vectors.
+// a <- coefficients of (a b - c) / Z_H from the three coset evaluation vectors.  The pointwise step is folded
+// into the load of the first transform pass, the canonical form into the store of the last one.
 void witness_map_quotient(Ctx* ctx, FrEl* a, const FrEl* b, const FrEl* c, uint32_t log_n, bool natural_out,
                           cudaStream_t st) {
   const NttDomain& d = ntt_domain(ctx, log_n);
   const FrEl* tw_ci = ntt_twiddles(ctx, log_n, TW_COSET_INV, st);
-  wm_pointwise(ctx, a, b, c, log_n, d.wm_k1, d.wm_k2, st);
-  ntt_dif(ctx, tw_ci, a, log_n, st);
+  if (log_n == 0) {
+    wm_pointwise(ctx, a, b, c, log_n, d.wm_k1, d.wm_k2, st);
+    fr_canonicalize(ctx, a, 1, st);
+    return;
+  }
+  const Plan p = make_plan(log_n);
+  for (int i = p.npass - 1; i >= 0; i--) {
+    PassArgs pa = pass_args(a, const_cast<FrEl*>(b), const_cast<FrEl*>(c), tw_ci, nullptr, p.pass[i]);
+    if (i == p.npass - 1) { pa.flags |= PF_POINTWISE_IN; pa.k1 = d.wm_k1; pa.k2 = d.wm_k2; }
+    if (i == 0 && !natural_out) pa.flags |= PF_CANONICAL_OUT;
+    launch_pass<PASS_DIF>(ctx, pa, log_n, 1, st);
+  }
   if (natural_out) ntt_bitrev(ctx, a, log_n, nullptr, nullptr, nullptr, st);
-  else fr_canonicalize(ctx, a, (size_t)1 << log_n, st);
 }
 
 void witness_map_device(Ctx* ctx, FrEl* a, FrEl* b, FrEl* c, uint32_t log_n, bool natural_out, cudaStream_t st) {
-  witness_map_transform(ctx, a, log_n, st);
-  witness_map_transform(ctx, b, log_n, st);
-  witness_map_transform(ctx, c, log_n, st);
+  witness_map_transform3(ctx, a, b, c, log_n, st);
   witness_map_quotient(ctx, a, b, c, log_n, natural_out, st);
+}
+
+// ---------------------------------------------------------------------------
+// Distributed witness map (point-sharded prover over W = 2^wbits GPUs).  Every rank holds n / W elements
+// of each vector.  Column-owned layout X: ownership bits [k0 - wbits, k0) (the rank owns 2^(k0 - wbits)
+// columns of the 2^k0 x 2^(log_n - k0) matrix) -- the high passes are local.  Row-owned layout Y: ownership
+// bits [log_n - wbits, log_n) (a contiguous chunk) -- the low pass is local.  A layout change is the store
+// of the pass before it, straight into the peers' buffers over NVLink; the caller puts a barrier between a
+// step that writes peers and the step that reads what was written.
+// ---------------------------------------------------------------------------
+bool ntt_dist_supported(uint32_t log_n, uint32_t wbits) {
+  if (wbits == 0 || wbits > 3 || log_n < 14 || log_n > 28) return false;
+  const Plan p = make_plan(log_n, wbits);
+  return p.k0 > wbits && log_n - p.k0 >= wbits;
+}
+uint32_t ntt_dist_col_bits(uint32_t log_n, uint32_t wbits) { return make_plan(log_n, wbits).k0 - wbits; }
+
+static void dist_fill(PassArgs& pa, const NttDist& D, uint32_t ob_in, uint32_t ob_out, FrEl* const* out_of_rank0,
+                      FrEl* const* out_of_rank1, FrEl* const* out_of_rank2) {
+  pa.ob_in = ob_in; pa.ob_out = ob_out; pa.wbits = D.wbits; pa.me = D.me;
+  if (ob_out != kNoDist)
+    for (uint32_t r = 0; r < (1u << D.wbits); r++) {
+      pa.peer[0][r] = out_of_rank0 ? out_of_rank0[r] : nullptr;
+      pa.peer[1][r] = out_of_rank1 ? out_of_rank1[r] : nullptr;
+      pa.peer[2][r] = out_of_rank2 ? out_of_rank2[r] : nullptr;
+    }
+}
+
+// step 1 (after the row evaluation into X): inverse-transform high passes on X_a, X_b, X_c; the last one
+// scatters into the peers' Y_a, Y_b, Y_c
+void wm_dist_step1(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st) {
+  const Plan p = make_plan(log_n, D.wbits);
+  const uint32_t obC = p.k0 - D.wbits, obR = log_n - D.wbits, ll = log_n - D.wbits;
+  const FrEl* tw_inv = ntt_twiddles(ctx, log_n, TW_INV, st);
+  for (int i = p.npass - 1; i >= 1; i--) {
+    PassArgs pa = pass_args(D.x[0], D.x[1], D.x[2], tw_inv, nullptr, p.pass[i]);
+    dist_fill(pa, D, obC, i == 1 ? obR : kNoDist, D.peer_y[0], D.peer_y[1], D.peer_y[2]);
+    launch_pass<PASS_DIF>(ctx, pa, ll, 3, st);
+  }
+}
+// step 2: fused low pass (inverse then coset-forward) on Y, scattering back into the peers' X
+void wm_dist_step2(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st) {
+  const Plan p = make_plan(log_n, D.wbits);
+  const uint32_t obC = p.k0 - D.wbits, obR = log_n - D.wbits, ll = log_n - D.wbits;
+  PassArgs pa = pass_args(D.y[0], D.y[1], D.y[2], ntt_twiddles(ctx, log_n, TW_INV, st),
+                          ntt_twiddles(ctx, log_n, TW_COSET_FWD, st), p.pass[0]);
+  dist_fill(pa, D, obR, obC, D.peer_x[0], D.peer_x[1], D.peer_x[2]);
+  launch_pass<PASS_DIF_DIT>(ctx, pa, ll, 3, st);
+}
+// step 3: coset-forward high passes on X (local), then the quotient (pointwise folded into the load) and the
+// coset-inverse high passes on X_a; the last one scatters into the peers' Y_a
+void wm_dist_step3(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st) {
+  const Plan p = make_plan(log_n, D.wbits);
+  const uint32_t obC = p.k0 - D.wbits, obR = log_n - D.wbits, ll = log_n - D.wbits;
+  const NttDomain& d = ntt_domain(ctx, log_n);
+  const FrEl* tw_cf = ntt_twiddles(ctx, log_n, TW_COSET_FWD, st);
+  const FrEl* tw_ci = ntt_twiddles(ctx, log_n, TW_COSET_INV, st);
+  for (int i = 1; i < p.npass; i++) {
+    PassArgs pa = pass_args(D.x[0], D.x[1], D.x[2], tw_cf, nullptr, p.pass[i]);
+    dist_fill(pa, D, obC, kNoDist, nullptr, nullptr, nullptr);
+    launch_pass<PASS_DIT>(ctx, pa, ll, 3, st);
+  }
+  for (int i = p.npass - 1; i >= 1; i--) {
+    PassArgs pa = pass_args(D.x[0], D.x[1], D.x[2], tw_ci, nullptr, p.pass[i]);
+    dist_fill(pa, D, obC, i == 1 ? obR : kNoDist, D.peer_y[0], nullptr, nullptr);
+    if (i == p.npass - 1) { pa.flags |= PF_POINTWISE_IN; pa.k1 = d.wm_k1; pa.k2 = d.wm_k2; }
+    launch_pass<PASS_DIF>(ctx, pa, ll, 1, st);
+  }
+}
+// step 4: coset-inverse low pass on Y_a: this rank's chunk [n me / W, n (me + 1) / W) of h in bit-reversed
+// order, canonical
+void wm_dist_step4(Ctx* ctx, const NttDist& D, uint32_t log_n, cudaStream_t st) {
+  const Plan p = make_plan(log_n, D.wbits);
+  const uint32_t obR = log_n - D.wbits, ll = log_n - D.wbits;
+  PassArgs pa = pass_args(D.y[0], nullptr, nullptr, ntt_twiddles(ctx, log_n, TW_COSET_INV, st), nullptr, p.pass[0]);
+  dist_fill(pa, D, obR, kNoDist, nullptr, nullptr, nullptr);
+  pa.flags |= PF_CANONICAL_OUT;
+  launch_pass<PASS_DIF>(ctx, pa, ll, 1, st);
 }
 
 // ---------------------------------------------------------------------------

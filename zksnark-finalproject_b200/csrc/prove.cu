@@ -331,9 +331,7 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
                           const uint64_t s[4], uint8_t* partial_out) {
   // issue order: everything light first (sorts, witness map, H sort), then the GPU-filling accumulations
   prove_begin(c, pk, d_z, r, s, /*with_accums=*/false);
-  witness_map_transform(&c, d_a, pk.log_n, c.stream);
-  witness_map_transform(&c, d_b, pk.log_n, c.stream);
-  witness_map_transform(&c, d_c, pk.log_n, c.stream);
+  witness_map_transform3(&c, d_a, d_b, d_c, pk.log_n, c.stream);
   prove_quotient(c, pk, d_a, d_b, d_c, /*with_h_finish=*/false);
   prove_accums(c, pk);
   prove_h_finish(c, pk);
@@ -400,6 +398,32 @@ void prove_partial_on_device_buffers(Ctx& c, const b2z_pk* pk, FrEl* d_a, FrEl* 
 }
 void prove_begin_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
   prove_begin(c, pk_of(c, pk, "b2z_groth16_shard_begin"), d_z, r, s);
+}
+// ---- pieces of a proof for the tile-sharded (distributed witness map) prover in r1cs.cu
+void prove_begin_sorts_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]) {
+  prove_begin(c, pk_of(c, pk, "b2z_dist_prove"), d_z, r, s, /*with_accums=*/false);
+}
+uint32_t pk_h_chunk(const b2z_pk* pk, uint32_t* h_lo) {
+  if (h_lo) *h_lo = pk->impl.h_lo;
+  return pk->impl.hn;
+}
+// d_h: this shard's hn coefficients of h (bit-reversed positions [h_lo, h_lo + hn)), canonical Montgomery form
+void prove_dist_h_sort_on(Ctx& c, const b2z_pk* pk, const FrEl* d_h, cudaStream_t st) {
+  PkImpl& P = pk_of(c, pk, "b2z_dist_prove");
+  fr_from_mont_device(&c, d_h, P.hc.p, P.hn, st);
+  msm_sort<G1>(&c, 0, P.h, P.hc.p, P.hn, nullptr, st);
+}
+// all five accumulations, chained, once `ready` (witness map + H sort done) has fired; then the host epilogue
+void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t ready, uint8_t* partial_out) {
+  PkImpl& P = pk_of(c, pk, "b2z_dist_prove");
+  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], ready, 0));      // the G2 accumulation opens the chain
+  B2Z_CUDA(cudaStreamWaitEvent(c.stream, ready, 0));      // H accumulates on the main stream
+  prove_accums(c, P);
+  prove_h_finish(c, P);
+  prove_end(c, P, partial_out);
+}
+void combine_partials_host(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]) {
+  combine_partials(partials, world, proof_out);
 }
 void pk_bind_assignment_flag(const b2z_pk* pk, bool* flag) { const_cast<b2z_pk*>(pk)->impl.assignment_flag = flag; }
 void prove_finish_on(Ctx& c, const b2z_pk* pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, uint8_t* partial_out) {

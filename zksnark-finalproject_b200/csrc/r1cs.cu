@@ -76,6 +76,34 @@ __global__ void spmv_kernel(const uint32_t* __restrict__ rp, const uint32_t* __r
   y[row] = Fr::reduce(acc);
 }
 
+// Row evaluation for ONE RANK of the tile-sharded witness map: local index li of the column-owned layout is
+// the global row index with the rank inserted at bits [ob, ob + wbits); every local slot is written (zero
+// beyond the rows).  grid.y selects the matrix.
+__global__ void r1cs_eval_dist_kernel(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ ci0,
+                                      const FrEl* __restrict__ cf0, const uint32_t* __restrict__ rp1,
+                                      const uint32_t* __restrict__ ci1, const FrEl* __restrict__ cf1,
+                                      const uint32_t* __restrict__ rp2, const uint32_t* __restrict__ ci2,
+                                      const FrEl* __restrict__ cf2, const FrEl* __restrict__ z, uint32_t nc, uint32_t l,
+                                      uint32_t ob, uint32_t wbits, uint32_t me, uint32_t nl, FrEl* a, FrEl* b, FrEl* c) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= nl) return;
+  const uint32_t row = ((li >> ob) << (ob + wbits)) | (me << ob) | (li & ((1u << ob) - 1));
+  const uint32_t which = blockIdx.y;
+  const uint32_t* rp = which == 0 ? rp0 : (which == 1 ? rp1 : rp2);
+  const uint32_t* ci = which == 0 ? ci0 : (which == 1 ? ci1 : ci2);
+  const FrEl* cf = which == 0 ? cf0 : (which == 1 ? cf1 : cf2);
+  FrEl* out = which == 0 ? a : (which == 1 ? b : c);
+  FrEl acc = Fr::zero();
+  if (row < nc) {
+    const uint32_t end = rp[row + 1];
+    for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, Fr::mul(ldg32(cf + k), ldg32(z + ci[k])));
+    acc = Fr::reduce(acc);
+  } else if (which == 0 && row < nc + l) {
+    acc = Fr::reduce(ldg32(z + (row - nc)));
+  }
+  out[li] = acc;
+}
+
 void upload_csr(CsrDev& d, const uint64_t* row_ptr, const uint32_t* cols, const uint64_t* coeffs, uint64_t nc,
                 uint64_t m, cudaStream_t st) {
   B2Z_REQUIRE(row_ptr != nullptr, B2Z_EINVAL, "b2z_r1cs_upload: NULL row_ptr");
@@ -316,6 +344,232 @@ b2z_status b2z_groth16_shard_finish(b2z_ctx* ctx, const b2z_pk* pk, uint64_t* d_
     B2Z_REQUIRE(pk && d_a && d_b && d_c && partial_out, B2Z_EINVAL, "b2z_groth16_shard_finish: NULL argument");
     prove_finish_on(c, pk, reinterpret_cast<FrEl*>(d_a), reinterpret_cast<const FrEl*>(d_b),
                     reinterpret_cast<const FrEl*>(d_c), partial_out);
+  });
+}
+
+
+// ---- tile-sharded prover: ONE proof by W = 2, 4 or 8 GPUs with the witness map itself distributed ----------------
+// (include/b200zk.h, b2z_dist_*).  Data moves by stores / copies into the peers' memory over NVLink; the only
+// synchronisation is a host-side barrier on a few words of caller-provided shared host memory.
+}  // extern "C"
+
+namespace b2z {
+namespace {
+constexpr uint32_t kFlagStride = 16;   // u32 words between two ranks' flags (one cache line each)
+constexpr size_t kPartial = B2Z_PARTIAL_BYTES;
+}  // namespace
+struct DistImpl {
+  const Ctx* owner = nullptr;
+  uint32_t rank = 0, world = 1, wbits = 0, log_n = 0;
+  uint64_t m = 0;
+  size_t nl = 0, z_bytes = 0, region_bytes = 0;
+  const b2z_pk* pk = nullptr;
+  b2z_r1cs* r1cs = nullptr;
+  DevBuf<uint8_t> region;                 // [ z (m x 32 B) | X_a X_b X_c | Y_a Y_b Y_c ]  (n / W elements each)
+  uint8_t* peer_region[8] = {};
+  bool peer_ipc[8] = {};
+  uint32_t* flags = nullptr;              // shared host memory: world x kFlagStride u32, then world x 1344 B
+  uint8_t* partials = nullptr;
+  uint32_t epoch = 0;
+  cudaStream_t wm_st = nullptr;
+  cudaEvent_t ev_ready = nullptr;
+  NttDist nd;
+  ~DistImpl() {
+    for (uint32_t p = 0; p < 8; p++)
+      if (peer_ipc[p] && peer_region[p]) cudaIpcCloseMemHandle(peer_region[p]);
+    if (wm_st) cudaStreamDestroy(wm_st);
+    if (ev_ready) cudaEventDestroy(ev_ready);
+  }
+  FrEl* z() const { return reinterpret_cast<FrEl*>(region.p); }
+  uint8_t* vec_of(uint8_t* base, int layout /*0 X, 1 Y*/, int v) const {
+    return base + z_bytes + ((size_t)layout * 3 + v) * nl * sizeof(FrEl);
+  }
+};
+namespace {
+void dist_barrier(DistImpl& D, const char* where) {
+  D.epoch++;
+  __atomic_store_n(D.flags + D.rank * kFlagStride, D.epoch, __ATOMIC_RELEASE);
+  uint64_t spins = 0;
+  for (uint32_t p = 0; p < D.world; p++) {
+    // wrap-safe: the peer's epoch has reached ours
+    while ((int32_t)(__atomic_load_n(D.flags + p * kFlagStride, __ATOMIC_ACQUIRE) - D.epoch) < 0) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if (++spins > (1ull << 33))
+        throw StatusError{B2Z_ECUDA, std::string("b2z_dist_prove: a peer rank did not reach the barrier after ") + where};
+    }
+  }
+}
+}  // namespace
+}  // namespace b2z
+
+struct b2z_dist {
+  DistImpl impl;
+};
+
+extern "C" {
+
+uint64_t b2z_dist_shared_bytes(uint32_t world) { return (uint64_t)world * (kFlagStride * 4 + kPartial); }
+
+b2z_status b2z_dist_create(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, uint32_t rank, uint32_t world, void* shared_host,
+                           b2z_dist** out) {
+  if (out) *out = nullptr;
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(pk && r && shared_host && out, B2Z_EINVAL, "b2z_dist_create: NULL argument");
+    B2Z_REQUIRE((world == 2 || world == 4 || world == 8) && rank < world, B2Z_EINVAL,
+                "b2z_dist_create: world must be 2, 4 or 8 and rank < world");
+    R1csImpl& R = r1cs_of(c, r, "b2z_dist_create");
+    B2Z_REQUIRE(pk_matches(pk, R.log_n, R.m, R.l), B2Z_EINVAL, "b2z_dist_create: key and matrices disagree");
+    uint32_t wbits = 0;
+    while ((1u << wbits) < world) wbits++;
+    B2Z_REQUIRE(ntt_dist_supported(R.log_n, wbits), B2Z_ESIZE,
+                "b2z_dist_create: domain too small for a tile-sharded witness map (use b2z_groth16_prove_partial_r1cs)");
+    uint32_t h_lo = 0;
+    const uint32_t hn = pk_h_chunk(pk, &h_lo);
+    const size_t n = (size_t)1 << R.log_n;
+    B2Z_REQUIRE(hn == n / world && h_lo == n / world * rank, B2Z_EINVAL,
+                "b2z_dist_create: the key must be shard `rank` of `world` (b2z_pk_upload_shard)");
+    std::unique_ptr<b2z_dist> d(new b2z_dist());
+    DistImpl& D = d->impl;
+    D.owner = &c; D.rank = rank; D.world = world; D.wbits = wbits; D.log_n = R.log_n; D.m = R.m;
+    D.pk = pk; D.r1cs = r;
+    D.nl = n / world;
+    D.z_bytes = ((R.m * sizeof(FrEl) + 255) / 256) * 256;
+    D.region_bytes = D.z_bytes + 6 * D.nl * sizeof(FrEl);
+    D.region.alloc(D.region_bytes);
+    B2Z_CUDA(cudaMemset(D.region.p, 0, D.region_bytes));
+    D.peer_region[rank] = D.region.p;
+    D.flags = static_cast<uint32_t*>(shared_host);
+    D.partials = static_cast<uint8_t*>(shared_host) + (size_t)world * kFlagStride * 4;
+    int lo = 0, hi = 0;
+    B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B2Z_CUDA(cudaStreamCreateWithPriority(&D.wm_st, cudaStreamNonBlocking, hi));
+    B2Z_CUDA(cudaEventCreateWithFlags(&D.ev_ready, cudaEventDisableTiming));
+    // warm the twiddle tables now: they are built lazily on first use
+    for (TwKind k : {TW_INV, TW_COSET_FWD, TW_COSET_INV}) ntt_twiddles(&c, R.log_n, k, D.wm_st);
+    B2Z_CUDA(cudaStreamSynchronize(D.wm_st));
+    *out = d.release();
+  });
+}
+
+void b2z_dist_destroy(b2z_ctx* ctx, b2z_dist* d) {
+  if (d == nullptr) return;
+  if (ctx != nullptr) {
+    std::lock_guard<std::mutex> lock(ctx->impl.mu);
+    cudaSetDevice(ctx->impl.device);
+    cudaDeviceSynchronize();
+  }
+  delete d;
+}
+
+b2z_status b2z_dist_export(b2z_ctx* ctx, b2z_dist* d, uint8_t ipc_handle[64], void** device_ptr) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(d && d->impl.owner == &c && (ipc_handle || device_ptr), B2Z_EINVAL, "b2z_dist_export: bad argument");
+    if (device_ptr) *device_ptr = d->impl.region.p;
+    if (ipc_handle) {
+      cudaIpcMemHandle_t h;
+      static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+      B2Z_CUDA(cudaIpcGetMemHandle(&h, d->impl.region.p));
+      std::memcpy(ipc_handle, &h, 64);
+    }
+  });
+}
+
+b2z_status b2z_dist_attach(b2z_ctx* ctx, b2z_dist* d, uint32_t peer, const uint8_t* ipc_handle, void* device_ptr) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(d && d->impl.owner == &c && peer < d->impl.world && (ipc_handle != nullptr) != (device_ptr != nullptr),
+                B2Z_EINVAL, "b2z_dist_attach: need a peer rank and exactly one of ipc_handle / device_ptr");
+    DistImpl& D = d->impl;
+    if (peer == D.rank) return;
+    if (device_ptr != nullptr) {
+      // same process: a plain device pointer; enable peer access when it lives on another GPU
+      cudaPointerAttributes at;
+      B2Z_CUDA(cudaPointerGetAttributes(&at, device_ptr));
+      if (at.device != c.device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) B2Z_CUDA(e);
+        cudaGetLastError();
+      }
+      D.peer_region[peer] = static_cast<uint8_t*>(device_ptr);
+    } else {
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, ipc_handle, 64);
+      void* p = nullptr;
+      B2Z_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      D.peer_region[peer] = static_cast<uint8_t*>(p);
+      D.peer_ipc[peer] = true;
+    }
+  });
+}
+
+b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* d, const uint64_t* z, int z_is_full_device_copy, const uint64_t rr[4],
+                          const uint64_t ss[4], uint8_t proof_out[192]) {
+  return guarded(ctx, [&](Ctx& c) {
+    B2Z_REQUIRE(d && d->impl.owner == &c && z && rr && ss && proof_out, B2Z_EINVAL, "b2z_dist_prove: bad argument");
+    DistImpl& D = d->impl;
+    for (uint32_t p = 0; p < D.world; p++)
+      B2Z_REQUIRE(D.peer_region[p] != nullptr, B2Z_EINVAL, "b2z_dist_prove: not every peer is attached (b2z_dist_attach)");
+    R1csImpl& R = r1cs_of(c, D.r1cs, "b2z_dist_prove");
+    cudaStream_t ws = D.wm_st;
+    // ---- the assignment: every rank moves 1 / W of it over PCIe and hands the slice to its peers over NVLink
+    if (z_is_full_device_copy) {
+      B2Z_CUDA(cudaMemcpyAsync(D.z(), z, D.m * sizeof(FrEl), cudaMemcpyDefault, ws));
+    } else {
+      const uint64_t lo = D.m * D.rank / D.world, hi = D.m * (D.rank + 1) / D.world;
+      const size_t off = lo * sizeof(FrEl), bytes = (hi - lo) * sizeof(FrEl);
+      B2Z_CUDA(cudaMemcpyAsync(D.region.p + off, reinterpret_cast<const uint8_t*>(z) + off, bytes, cudaMemcpyDefault, ws));
+      for (uint32_t k = 1; k < D.world; k++) {
+        const uint32_t p = (D.rank + k) % D.world;
+        B2Z_CUDA(cudaMemcpyAsync(D.peer_region[p] + off, D.region.p + off, bytes, cudaMemcpyDefault, ws));
+      }
+      B2Z_CUDA(cudaStreamSynchronize(ws));
+      dist_barrier(D, "the assignment exchange");
+    }
+    B2Z_CUDA(cudaEventRecord(R.ev_z, ws));
+    // ---- light z-only work on the auxiliary streams: scalar conversion and the four sorts
+    B2Z_CUDA(cudaStreamWaitEvent(c.aux[0], R.ev_z, 0));
+    prove_begin_sorts_on(c, D.pk, D.z(), rr, ss);
+    // ---- tile-sharded witness map on its own high-priority stream
+    NttDist& nd = D.nd;
+    nd.wbits = D.wbits; nd.me = D.rank;
+    for (int v = 0; v < 3; v++) {
+      nd.x[v] = reinterpret_cast<FrEl*>(D.vec_of(D.region.p, 0, v));
+      nd.y[v] = reinterpret_cast<FrEl*>(D.vec_of(D.region.p, 1, v));
+      for (uint32_t p = 0; p < D.world; p++) {
+        nd.peer_x[v][p] = reinterpret_cast<FrEl*>(D.vec_of(D.peer_region[p], 0, v));
+        nd.peer_y[v][p] = reinterpret_cast<FrEl*>(D.vec_of(D.peer_region[p], 1, v));
+      }
+    }
+    {
+      ProfileScope ps(&c, PH_R1CS_EVAL, ws, 3 * D.nl);
+      const dim3 grid((uint32_t)((D.nl + 127) / 128), 3);
+      r1cs_eval_dist_kernel<<<grid, 128, 0, ws>>>(R.mat[0].row_ptr.p, R.mat[0].cols.p, R.mat[0].coeffs.p, R.mat[1].row_ptr.p,
+                                                 R.mat[1].cols.p, R.mat[1].coeffs.p, R.mat[2].row_ptr.p, R.mat[2].cols.p,
+                                                 R.mat[2].coeffs.p, D.z(), (uint32_t)R.nc, (uint32_t)R.l,
+                                                 ntt_dist_col_bits(D.log_n, D.wbits), D.wbits, D.rank, (uint32_t)D.nl, nd.x[0],
+                                                 nd.x[1], nd.x[2]);
+      B2Z_LAUNCHED(&c);
+    }
+    wm_dist_step1(&c, nd, D.log_n, ws);
+    B2Z_CUDA(cudaStreamSynchronize(ws));
+    dist_barrier(D, "witness-map step 1");
+    wm_dist_step2(&c, nd, D.log_n, ws);
+    B2Z_CUDA(cudaStreamSynchronize(ws));
+    dist_barrier(D, "witness-map step 2");
+    wm_dist_step3(&c, nd, D.log_n, ws);
+    B2Z_CUDA(cudaStreamSynchronize(ws));
+    dist_barrier(D, "witness-map step 3");
+    wm_dist_step4(&c, nd, D.log_n, ws);
+    prove_dist_h_sort_on(c, D.pk, nd.y[0], ws);
+    B2Z_CUDA(cudaEventRecord(D.ev_ready, ws));
+    // ---- the five accumulations back to back, host epilogue of this shard
+    prove_dist_finish_on(c, D.pk, D.ev_ready, D.partials + (size_t)D.rank * kPartial);
+    // ---- partial sums meet in the shared host memory; every rank combines
+    dist_barrier(D, "the accumulations");
+    combine_partials_host(D.partials, D.world, proof_out);
+    // nobody may overwrite its partial (next proof) before every rank has combined
+    dist_barrier(D, "the combine");
   });
 }
 

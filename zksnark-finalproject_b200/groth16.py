@@ -406,6 +406,88 @@ class ProvingKey:
         self._handle = None
 
 
+
+class DistributedProver:
+    """One rank of the tile-sharded prover (b2z_dist_*): ONE proof by 2, 4 or 8 GPUs, witness map included.
+    `pk` must be uploaded as shard `rank` of `world` through `ctx`, `cm` uploaded through `ctx`.
+    `shared`: a writable buffer of b2z_dist_shared_bytes(world) zeroed bytes visible to every rank (numpy array
+    for threads of one process, multiprocessing.shared_memory between processes)."""
+
+    def __init__(self, ctx, pk, cm, rank, world, shared):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        L = ctx._lib
+        self._shared = shared                       # keep alive
+        buf = np.frombuffer(shared, dtype=np.uint8) if not isinstance(shared, np.ndarray) else shared
+        if buf.nbytes < L.b2z_dist_shared_bytes(self.world):
+            raise ValueError("shared buffer smaller than b2z_dist_shared_bytes(world)")
+        self._buf = buf
+        pk.upload(ctx, rank=rank, world=world)
+        cm.upload(ctx)
+        h = ctypes.c_void_p()
+        ctx.check(L.b2z_dist_create(ctx.handle, pk._handle, cm._handle, self.rank, self.world, _ptr(buf), ctypes.byref(h)))
+        self.handle = h
+        self._keep = (pk, cm)
+
+    @staticmethod
+    def shared_bytes(world):
+        return int(_ffi.lib().b2z_dist_shared_bytes(int(world)))
+
+    def export(self):
+        """(64-byte CUDA IPC handle, device pointer) of this rank's exchange region."""
+        ipc = np.zeros(64, dtype=np.uint8)
+        ptr = ctypes.c_void_p()
+        self.ctx.check(self.ctx._lib.b2z_dist_export(self.ctx.handle, self.handle, _ptr(ipc), ctypes.byref(ptr)))
+        return ipc.tobytes(), int(ptr.value)
+
+    def attach(self, peer, ipc_handle=None, device_ptr=None):
+        ipc = np.frombuffer(ipc_handle, dtype=np.uint8).copy() if ipc_handle is not None else None
+        self.ctx.check(self.ctx._lib.b2z_dist_attach(self.ctx.handle, self.handle, int(peer), _ptr(ipc),
+                                                     ctypes.c_void_p(device_ptr) if device_ptr is not None else None))
+
+    def prove(self, z, r, s, resident=False):
+        """All ranks call this for the same proof (same r, s; canonical ints).  z: (m, 4) uint64 host array of
+        Montgomery limbs, or an integer device address; resident=True: z is a full device copy on this rank."""
+        zp = ctypes.c_void_p(int(z)) if isinstance(z, int) else _ptr(_fr_array(z))
+        rs = codec.fr_to_mont_limbs([r, s])
+        out = np.zeros(192, dtype=np.uint8)
+        self.ctx.check(self.ctx._lib.b2z_dist_prove(self.ctx.handle, self.handle, zp, int(bool(resident)), _ptr(rs[0:1]),
+                                                    _ptr(rs[1:2]), _ptr(out)))
+        return out.tobytes()
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self.ctx._lib.b2z_dist_destroy(self.ctx.handle, self.handle)
+        self.handle = None
+
+    @classmethod
+    def over_torch_distributed(cls, ctx, pk, cm, group=None):
+        """One process per GPU (torchrun): the shared host buffer is POSIX shared memory created by rank 0, the
+        exchange regions are attached by CUDA IPC handle; torch.distributed only carries the set-up messages."""
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = cls.shared_bytes(world)
+        name = [None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            shm.buf[:nbytes] = bytes(nbytes)
+            name[0] = shm.name
+        dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        self = cls(ctx, pk, cm, rank, world, np.ndarray((nbytes,), dtype=np.uint8, buffer=shm.buf))
+        self._shm = shm
+        handles = [None] * world
+        dist.all_gather_object(handles, self.export()[0], group=group)
+        for p in range(world):
+            if p != rank:
+                self.attach(p, ipc_handle=handles[p])
+        dist.barrier(group=group)
+        if rank == 0:
+            shm.unlink()                            # the mapping stays valid in every attached process
+        return self
+
+
 class VerifyingKey:
     """ark_groth16::VerifyingKey<Bls12_381> (limb arrays; only what verification needs)."""
 
