@@ -266,6 +266,7 @@ class Bench:
         cm.upload(ctx)
         proof = np.zeros(192, dtype=np.uint8)
         res = {}
+        dp = None
 
         if world == 1:
             pk.upload(ctx)
@@ -279,40 +280,61 @@ class Bench:
             step_e2e = lambda: step(z_host)
             collective = None
         else:
-            # ---- ONE proof by all ranks: every rank holds 1/N of every base set; the three input transforms
-            # of the witness map are done once in the group (rank j % N owns matrix j) and broadcast
+            # ---- ONE proof by all ranks (b2z_dist_*): every rank holds 1/N of every base set AND 1/N of every
+            # witness-map vector; layout changes are peer stores over NVLink fused into the transform passes, the
+            # assignment moves 1/N per rank over PCIe + NVLink, partial sums meet in shared host memory
             dist = self.dist
             spk = pk.upload(ctx, rank=rank, world=world)
             r, s = proof_scalars(0)                                            # the same r, s on every rank
             rs = codec.fr_to_mont_limbs([r, s])
-            bufs = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
-            owners = [j % world for j in range(3)]
-            part = np.zeros(pkg._ffi.PARTIAL_BYTES, dtype=np.uint8)
-            gathered = [torch.empty(pkg._ffi.PARTIAL_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
-            out = {}
+            dp = None
+            try:
+                dp = pkg.DistributedProver.over_torch_distributed(ctx, spk, cm)
+            except Exception as e:                                             # domain too small to tile / no IPC
+                log("tile-sharded prover unavailable (%r): falling back to replicated transforms + NCCL" % (e,))
+            ok = torch.tensor([1 if dp is not None else 0], device="cuda")
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and dp is not None:
+                dp.close()
+                dp = None
+            if dp is not None:
+                def step(zt, resident):
+                    ctx.check(L.b2z_dist_prove(ctx.handle, dp.handle, hp(zt), int(resident), p(rs[0:1]), p(rs[1:2]),
+                                               p(proof)))
+                step_value = lambda: step(z_dev, True)
+                step_e2e = lambda: step(z_host, False)
+                collective = ("peer-memory stores over NVLink: assignment slices (%d KB per rank) + 3 fused "
+                              "transform/transpose exchanges (<= %d MB per rank each); partial sums (%d B per rank) "
+                              "through shared host memory; no NCCL in the data path"
+                              % (m * 32 // world // 1024, 3 * n * 32 // world // (1 << 20), pkg._ffi.PARTIAL_BYTES))
+            else:
+                bufs = [torch.empty((n, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+                owners = [j % world for j in range(3)]
+                part = np.zeros(pkg._ffi.PARTIAL_BYTES, dtype=np.uint8)
+                gathered = [torch.empty(pkg._ffi.PARTIAL_BYTES, dtype=torch.uint8, device="cuda") for _ in range(world)]
 
-            def step(zt):
-                uploaded = False
-                for j in range(3):
-                    if owners[j] == rank:
-                        ctx.check(L.b2z_r1cs_coset_evals(ctx.handle, cm._handle, j, None if uploaded else hp(zt),
-                                                         hp(bufs[j])))
-                        uploaded = True
-                works = [dist.broadcast(bufs[j], src=owners[j], async_op=True) for j in range(3)]
-                ctx.check(L.b2z_groth16_shard_begin(ctx.handle, spk._handle, cm._handle, None if uploaded else hp(zt),
-                                                    p(rs[0:1]), p(rs[1:2])))
-                for w in works:
-                    w.wait()
-                torch.cuda.current_stream().synchronize()      # the library works on its own streams
-                ctx.check(L.b2z_groth16_shard_finish(ctx.handle, spk._handle, hp(bufs[0]), hp(bufs[1]), hp(bufs[2]),
-                                                     p(part)))
-                dist.all_gather(gathered, torch.from_numpy(part).cuda())
-                out["proof"] = pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered])
-                proof[:] = np.frombuffer(out["proof"], dtype=np.uint8)
-            step_value = lambda: step(z_dev)
-            step_e2e = lambda: step(z_host)
-            collective = ("3 NCCL broadcasts of %d MB (coset evaluations) + all_gather of %d B per rank"
-                          % (n * 32 // (1 << 20), pkg._ffi.PARTIAL_BYTES))
+                def step(zt, resident):
+                    uploaded = False
+                    for j in range(3):
+                        if owners[j] == rank:
+                            ctx.check(L.b2z_r1cs_coset_evals(ctx.handle, cm._handle, j, None if uploaded else hp(zt),
+                                                             hp(bufs[j])))
+                            uploaded = True
+                    works = [dist.broadcast(bufs[j], src=owners[j], async_op=True) for j in range(3)]
+                    ctx.check(L.b2z_groth16_shard_begin(ctx.handle, spk._handle, cm._handle,
+                                                        None if uploaded else hp(zt), p(rs[0:1]), p(rs[1:2])))
+                    for w in works:
+                        w.wait()
+                    torch.cuda.current_stream().synchronize()      # the library works on its own streams
+                    ctx.check(L.b2z_groth16_shard_finish(ctx.handle, spk._handle, hp(bufs[0]), hp(bufs[1]), hp(bufs[2]),
+                                                         p(part)))
+                    dist.all_gather(gathered, torch.from_numpy(part).cuda())
+                    proof[:] = np.frombuffer(pkg.Groth16.combine([bytes(g.cpu().numpy().tobytes()) for g in gathered]),
+                                             dtype=np.uint8)
+                step_value = lambda: step(z_dev, True)
+                step_e2e = lambda: step(z_host, False)
+                collective = ("3 NCCL broadcasts of %d MB (coset evaluations) + all_gather of %d B per rank"
+                              % (n * 32 // (1 << 20), pkg._ffi.PARTIAL_BYTES))
 
         # ---- correctness of what is being timed (outside the timed region)
         step_value()
@@ -335,6 +357,8 @@ class Bench:
         units = (ctypes.c_uint64 * 8)()
         ctx.check(L.b2z_profile_read(ctx.handle, ms, cnt, units, 1))
         L.b2z_profile_enable(ctx.handle, 0)
+        if os.environ.get("B2Z_TIMELINE"):
+            self.dump_timeline(step_value, "%s_n%d_rank%d" % (name, world, rank))
         for _ in range(warmup):
             step_e2e()
         e2e_dev_s, e2e_wall_s = self.timed(step_e2e, steps)
@@ -342,6 +366,8 @@ class Bench:
 
         # ---- replicas (N > 1): one independent proof per GPU, no data-path collective
         replicas = None
+        if world > 1 and dp is not None:
+            dp.close()
         if world > 1 and main:
             pk.free()
             fpk = pkg.ProvingKey(pk.num_variables, pk.num_instance, pk.domain_size, pk.a_query, pk.b_g1_query,
@@ -384,9 +410,9 @@ class Bench:
             "config": config_of(name, inst, world), "value": 1.0 / per_step, "ms_per_step": per_step * 1e3,
             "wall_ms_per_step": wall_s / steps * 1e3, "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": steps / e2e_dev_s, "unit": "proofs/s", "ms_per_step": e2e_dev_s / steps * 1e3,
-                    "h2d_bytes_per_step": int(m * 32 + 64) * world, "d2h_bytes_per_step": 1344 * world,
-                    "call": ("b2z_groth16_prove_r1cs" if world == 1 else
-                             "b2z_r1cs_coset_evals + b2z_groth16_shard_begin/finish + b2z_groth16_combine on every rank")
+                    "h2d_bytes_per_step": int(m * 32 + 64) if world == 1 else int(m * 32 + 64 * world),
+                    "d2h_bytes_per_step": 1344 * world,
+                    "call": ("b2z_groth16_prove_r1cs" if world == 1 else "b2z_dist_prove on every rank")
                             + ", z in pinned host memory (row evaluation + witness map + 5 MSMs + host epilogue)"},
             "collective": collective, "replicas": replicas,
         })
@@ -422,6 +448,33 @@ class Bench:
             pk.free()
         cm.free()
         return res
+
+    def dump_timeline(self, step, tag):
+        """Development aid (B2Z_TIMELINE=dir): CUDA-event spans of ONE proof on this rank, relative to the first."""
+        L, ctx = self.L, self.ctx
+        self.barrier()
+        L.b2z_profile_enable(ctx.handle, 1)
+        t0 = time.perf_counter()
+        step()
+        wall = (time.perf_counter() - t0) * 1e3
+        N = 4096
+        ph = (ctypes.c_int * N)()
+        a = (ctypes.c_double * N)()
+        b = (ctypes.c_double * N)()
+        n = L.b2z_profile_spans(ctx.handle, N, ph, a, b)
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_uint64 * 8)()
+        units = (ctypes.c_uint64 * 8)()
+        L.b2z_profile_read(ctx.handle, ms, cnt, units, 1)
+        L.b2z_profile_enable(ctx.handle, 0)
+        names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
+        base = min(a[i] for i in range(n)) if n else 0.0
+        rows = [{"phase": names[ph[i]], "start_ms": a[i] - base, "stop_ms": b[i] - base}
+                for i in sorted(range(n), key=lambda i: a[i])]
+        out = os.environ["B2Z_TIMELINE"]
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "timeline_%s.json" % tag), "w") as f:
+            json.dump({"wall_ms": wall, "spans": rows}, f, indent=0)
 
     def key_bytes(self, n, m):
         L = self.L

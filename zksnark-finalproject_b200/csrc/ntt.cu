@@ -202,7 +202,7 @@ enum PassMode { PASS_DIF = 0, PASS_DIT = 1, PASS_DIF_DIT = 2 };
 // grid = (n_local / 2^(k+logC) tiles, vectors); block = max(32, tile/8) threads;
 // dynamic smem = 2 * (S + S/8) * 16 bytes.
 template <int MODE, bool DIST>
-__global__ void __launch_bounds__(256) ntt_pass_kernel(const __grid_constant__ PassArgs a) {
+__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const __grid_constant__ PassArgs a) {
   extern __shared__ uint4 smem[];
   const PassGeom g = a.g;
   const uint32_t S = 1u << (g.k + g.logC);

@@ -64,6 +64,20 @@ __global__ void pack_flags_kernel2(const uint32_t* flags, uint32_t n, uint32_t* 
 
 inline uint32_t nblk(uint64_t n, uint32_t t) { return (uint32_t)((n + t - 1) / t); }
 
+constexpr uint32_t kCycBlock = 64;   // variables per block of the block-cyclic point sharding
+
+// local variable j of a block-cyclic shard -> global variable index
+__host__ __device__ inline uint64_t cyc_global(uint64_t j, uint32_t rank, uint32_t world) {
+  return ((j / kCycBlock) * world + rank) * kCycBlock + (j % kCycBlock);
+}
+// zc[j] = canonical integer of z[global(j)]: this shard's MSM scalars
+__global__ void fr_from_mont_cyclic_kernel(const FrEl* __restrict__ z, FrEl* zc, uint32_t count, uint32_t rank,
+                                           uint32_t world) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= count) return;
+  zc[j] = Fr::from_mont(z[cyc_global(j, rank, world)]);
+}
+
 FrEl fr_load_host(const uint64_t v[4]) {
   FrEl x;
   std::memcpy(x.l, v, 32);
@@ -80,11 +94,16 @@ struct PkImpl {
   // uploaded through.  Every entry point checks this and returns B2Z_EINVAL for a foreign context.
   const Ctx* owner = nullptr;
   bool* assignment_flag = nullptr;   // b2z_groth16_shard_begin .. shard_finish window (r1cs.cu)
+  cudaStream_t h_stream = nullptr;   // where the H accumulation of the proof in flight runs
   uint32_t log_n = 0;
   uint64_t m = 0, l = 0;
-  // shard: variables [lo, lo+ma) of the a/b queries, [l_lo, l_lo+ml) of the witness part, bit-reversed
-  // h positions [h_lo, h_lo+hn); alpha/beta/delta terms on shard 0 only
-  uint32_t lo = 0, ma = 0, l_lo = 0, ml = 0, h_lo = 0, hn = 0, with_vk = 1;
+  // shard: `ma` variables of the a/b queries -- either the contiguous range [lo, lo+ma) (cyc_world == 0) or,
+  // block-cyclic, the blocks cyc_rank, cyc_rank + cyc_world, ... of kCycBlock variables (balanced whatever the
+  // witness structure: Groth16 assignments have long stretches of small / Boolean values); the first l_skip of
+  // them are instance variables (not in l_query), ml = ma - l_skip; bit-reversed h positions [h_lo, h_lo+hn);
+  // alpha/beta/delta terms on shard 0 only
+  uint32_t lo = 0, ma = 0, l_skip = 0, ml = 0, h_lo = 0, hn = 0, with_vk = 1;
+  uint32_t cyc_world = 0, cyc_rank = 0;
   MsmBases<G1> a_set;          // [a_query  | alpha_1 delta_1]
   MsmBases<G1> b1_set;         // [b_g1     | beta_1  delta_1]
   MsmBases<G1> l_set;          // [l_query  | delta_1]
@@ -243,9 +262,15 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
   one_c.l[0] = 1;
   const FrEl tail_h[5] = {one_c, pk.r_c, one_c, pk.s_c, neg_rs};      // A: {1, r}; B1, B: {1, s}; L: {-rs}
   B2Z_CUDA(cudaMemcpyAsync(pk.tail.p, tail_h, sizeof(tail_h), cudaMemcpyHostToDevice, sA));
-  fr_from_mont_device(&c, d_z + pk.lo, pk.zc.p, pk.ma, sA);     // this shard's slice of z as canonical integers
+  // this shard's variables of z as canonical integers
+  if (pk.cyc_world == 0) {
+    fr_from_mont_device(&c, d_z + pk.lo, pk.zc.p, pk.ma, sA);
+  } else if (pk.ma) {
+    fr_from_mont_cyclic_kernel<<<nblk(pk.ma, 256), 256, 0, sA>>>(d_z, pk.zc.p, pk.ma, pk.cyc_rank, pk.cyc_world);
+    B2Z_LAUNCHED(&c);
+  }
   B2Z_CUDA(cudaEventRecord(pk.ev_z, sA));
-  const FrEl* z_l = pk.zc.p + (pk.l_lo - pk.lo);
+  const FrEl* z_l = pk.zc.p + pk.l_skip;
   // ---- the four z-only sorts, concurrently
   msm_sort<G1>(&c, 1, pk.a_set, pk.zc.p, pk.ma, pk.tail.p + 0, sA);
   B2Z_CUDA(cudaEventRecord(pk.ev_sorted[0], sA));
@@ -293,9 +318,10 @@ void prove_accums(Ctx& c, PkImpl& pk) {
 }
 
 // d_a, d_b, d_c: evaluations of the three QAP combinations on the coset g H (d_a is clobbered)
-void prove_h_finish(Ctx& c, PkImpl& pk) {
+void prove_h_finish(Ctx& c, PkImpl& pk, cudaStream_t st = nullptr) {
   const bool chain = (uint64_t)pk.h.n * pk.h.windows >= (1u << 16);
-  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, c.stream, chain ? pk.ev_accum[2] : nullptr, nullptr, &pk.hp[4]);
+  pk.h_stream = st ? st : c.stream;
+  msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, pk.h_stream, chain ? pk.ev_accum[2] : nullptr, nullptr, &pk.hp[4]);
 }
 void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, bool with_h_finish = true) {
   cudaStream_t st = c.stream;
@@ -322,7 +348,7 @@ void prove_end(Ctx& c, PkImpl& pk, uint8_t* partial_out) {
       pk.h_out + 5 * kG1Bytes / 4);
   B2Z_CUDA(cudaEventSynchronize(pk.ev_done[3]));
   host::g1_to_device_layout(g1_result(3), pk.h_out + 3 * kG1Bytes / 4);
-  B2Z_CUDA(cudaStreamSynchronize(c.stream));
+  B2Z_CUDA(cudaStreamSynchronize(pk.h_stream ? pk.h_stream : c.stream));
   host::g1_to_device_layout(g1_result(4), pk.h_out + 4 * kG1Bytes / 4);
   std::memcpy(partial_out, pk.h_out, kPartialBytes);
 }
@@ -413,13 +439,14 @@ void prove_dist_h_sort_on(Ctx& c, const b2z_pk* pk, const FrEl* d_h, cudaStream_
   fr_from_mont_device(&c, d_h, P.hc.p, P.hn, st);
   msm_sort<G1>(&c, 0, P.h, P.hc.p, P.hn, nullptr, st);
 }
-// all five accumulations, chained, once `ready` (witness map + H sort done) has fired; then the host epilogue
-void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t ready, uint8_t* partial_out) {
+// all five accumulations, chained: the first once `wm_done` has fired (the witness map's transform kernels need the
+// SMs the accumulations would fill), H on `h_st` -- the stream its sort was queued on, which therefore hides under
+// the other accumulations; then the host epilogue
+void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t wm_done, cudaStream_t h_st, uint8_t* partial_out) {
   PkImpl& P = pk_of(c, pk, "b2z_dist_prove");
-  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], ready, 0));      // the G2 accumulation opens the chain
-  B2Z_CUDA(cudaStreamWaitEvent(c.stream, ready, 0));      // H accumulates on the main stream
+  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], wm_done, 0));    // the G2 accumulation opens the chain
   prove_accums(c, P);
-  prove_h_finish(c, P);
+  prove_h_finish(c, P, h_st);
   prove_end(c, P, partial_out);
 }
 void combine_partials_host(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]) {
@@ -459,8 +486,10 @@ b2z_status b2z_fixed_base_mul_g2(b2z_ctx* ctx, const uint64_t* scalars, uint64_t
   return guarded(ctx, [&](Ctx& c) { fixed_base_entry<G2>(c, scalars, n, out_points, out_inf); });
 }
 
-b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from, uint32_t to, uint32_t den,
-                               b2z_pk** out) {
+// from / to / den: contiguous slice of the variables AND of the h positions.  cyc_world > 0: the h positions still
+// follow from / to / den, the variables are the block-cyclic subset of rank cyc_rank of cyc_world.
+static b2z_status pk_upload_impl(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from, uint32_t to, uint32_t den,
+                                 uint32_t cyc_rank, uint32_t cyc_world, b2z_pk** out) {
   if (out) *out = nullptr;
   return guarded(ctx, [&](Ctx& c) {
     B2Z_REQUIRE(d != nullptr && out != nullptr, B2Z_EINVAL, "b2z_pk_upload: NULL argument");
@@ -480,35 +509,74 @@ b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from
     P.log_n = d->log_domain;
     P.m = m;
     P.l = l;
-    // contiguous shards: variables [m from / den, m to / den), same fraction of the h positions
-    const uint64_t lo = m * from / den, hi = m * to / den;
-    const uint64_t l_lo = lo > l ? lo : l, l_hi = hi > l ? hi : l;      // witness variables in the slice
+    // the variables of this shard, in local order
+    if (cyc_world > 0 && l > kCycBlock) cyc_world = 0;   // the instance variables must sit in block 0
+    uint64_t lo = m * from / den, hi = m * to / den;
+    std::vector<uint32_t> ids;                           // cyclic mode only
+    if (cyc_world > 0) {
+      for (uint64_t b = cyc_rank; b * kCycBlock < m; b += cyc_world)
+        for (uint64_t i = b * kCycBlock; i < (b + 1) * kCycBlock && i < m; i++) ids.push_back((uint32_t)i);
+      P.cyc_world = cyc_world; P.cyc_rank = cyc_rank;
+      P.lo = 0; P.ma = (uint32_t)ids.size();
+      P.l_skip = cyc_rank == 0 ? (uint32_t)(l < P.ma ? l : P.ma) : 0;
+      lo = 0; hi = P.ma;
+    } else {
+      const uint64_t l_lo = lo > l ? lo : l;             // first witness variable in the slice
+      P.lo = (uint32_t)lo; P.ma = (uint32_t)(hi - lo);
+      P.l_skip = (uint32_t)((l_lo < hi ? l_lo : hi) - lo);
+    }
+    P.ml = P.ma - P.l_skip;
     const uint64_t h_lo = n * from / den, h_hi = n * to / den;
-    P.lo = (uint32_t)lo; P.ma = (uint32_t)(hi - lo);
-    P.l_lo = (uint32_t)l_lo; P.ml = (uint32_t)(l_hi - l_lo);
     P.h_lo = (uint32_t)h_lo; P.hn = (uint32_t)(h_hi - h_lo);
     P.with_vk = from == 0 ? 1u : 0u;
     cudaStream_t st = c.stream;
     size_t free_b = 0, total_b = 0;
     B2Z_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const bool pre = pk_precompute_bytes(d) / den * (to - from) < free_b / 2;
-    auto sub_inf = [](const uint8_t* inf, uint64_t from, uint64_t count, std::vector<uint8_t>& tmp) -> const uint8_t* {
-      if (inf == nullptr) return nullptr;
-      tmp.assign((count + 7) / 8 + 1, 0);
-      for (uint64_t i = 0; i < count; i++)
-        if ((inf[(from + i) >> 3] >> ((from + i) & 7)) & 1) tmp[i >> 3] |= (uint8_t)(1u << (i & 7));
-      return tmp.data();
+    // `count` points of a query, starting at local variable `skip` of this shard, as one contiguous host array
+    // (query index = variable index - shift) + identity bits; contiguous shards point straight into the caller's array
+    struct Picked {
+      const uint64_t* pts = nullptr;
+      const uint8_t* inf = nullptr;
+      std::vector<uint64_t> own_pts;
+      std::vector<uint8_t> own_inf;
     };
-    // one G1 set = `count` query points from `from`, then up to two vk points (shard 0 only)
-    auto build_g1 = [&](MsmBases<G1>& out, const uint64_t* query, const uint8_t* inf, uint64_t from, uint64_t count,
-                        const uint64_t* extra0, const uint64_t* extra1) {
+    auto pick = [&](Picked& out, const uint64_t* query, const uint8_t* inf, uint32_t skip, uint32_t count, uint64_t shift,
+                    uint32_t limbs) {
+      if (count == 0 || query == nullptr) return;
+      auto var = [&](uint32_t j) { return cyc_world > 0 ? (uint64_t)ids[j] : lo + j; };
+      if (cyc_world == 0) {
+        out.pts = query + (size_t)limbs * (var(skip) - shift);
+      } else {
+        out.own_pts.resize((size_t)limbs * count);
+        for (uint32_t j = 0; j < count;) {               // copy block by block
+          const uint64_t q = var(skip + j) - shift;
+          uint32_t run = 1;
+          while (j + run < count && var(skip + j + run) - shift == q + run) run++;
+          std::memcpy(&out.own_pts[(size_t)limbs * j], query + (size_t)limbs * q, (size_t)limbs * 8 * run);
+          j += run;
+        }
+        out.pts = out.own_pts.data();
+      }
+      if (inf != nullptr) {
+        out.own_inf.assign((count + 7) / 8 + 1, 0);
+        for (uint32_t j = 0; j < count; j++) {
+          const uint64_t q = var(skip + j) - shift;
+          if ((inf[q >> 3] >> (q & 7)) & 1) out.own_inf[j >> 3] |= (uint8_t)(1u << (j & 7));
+        }
+        out.inf = out.own_inf.data();
+      }
+    };
+    // one G1 set = the picked query points, then up to two vk points (shard 0 only)
+    auto build_g1 = [&](MsmBases<G1>& out, const uint64_t* query, const uint8_t* inf, uint32_t skip, uint32_t count,
+                        uint64_t shift, const uint64_t* extra0, const uint64_t* extra1) {
       const uint32_t extras = P.with_vk ? ((extra0 ? 1 : 0) + (extra1 ? 1 : 0)) : 0;
-      const uint32_t total = (uint32_t)count + extras;
+      const uint32_t total = count + extras;
       DevBuf<G1::Affine> dpts(total ? total : 1);
       std::vector<uint32_t> words((total + 31) / 32 + 1, 0u);
-      std::vector<uint8_t> tmp;
-      stage_points<G1::Affine>(dpts.p, words, 0, query ? query + 12 * from : nullptr, sub_inf(inf, from, count, tmp),
-                               count, st);
+      Picked pk_pts;
+      pick(pk_pts, query, inf, skip, count, shift, 12);
+      stage_points<G1::Affine>(dpts.p, words, 0, pk_pts.pts, pk_pts.inf, count, st);
       uint64_t at = count;
       if (P.with_vk && extra0) stage_points<G1::Affine>(dpts.p, words, at++, extra0, nullptr, 1, st);
       if (P.with_vk && extra1) stage_points<G1::Affine>(dpts.p, words, at++, extra1, nullptr, 1, st);
@@ -517,23 +585,17 @@ b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from
       msm_bases_build<G1>(&c, out, dpts.p, dinf.p, total, pre, 0, st);
       B2Z_CUDA(cudaStreamSynchronize(st));
     };
-    build_g1(P.a_set, d->a_query, d->a_inf, lo, P.ma, d->alpha_g1, d->delta_g1);
-    build_g1(P.b1_set, d->b_g1_query, d->b_g1_inf, lo, P.ma, d->beta_g1, d->delta_g1);
-    build_g1(P.l_set, d->l_query, d->l_inf, l_lo - l, P.ml, d->delta_g1, nullptr);
+    build_g1(P.a_set, d->a_query, d->a_inf, 0, P.ma, 0, d->alpha_g1, d->delta_g1);
+    build_g1(P.b1_set, d->b_g1_query, d->b_g1_inf, 0, P.ma, 0, d->beta_g1, d->delta_g1);
+    build_g1(P.l_set, d->l_query, d->l_inf, P.l_skip, P.ml, l, d->delta_g1, nullptr);
     {
       // G2: [b2 | beta_2 delta_2]
       const uint32_t n2 = P.ma + (P.with_vk ? 2 : 0);
       DevBuf<G2::Affine> dpts(n2 ? n2 : 1);
       std::vector<uint32_t> words((n2 + 31) / 32 + 1, 0u);
-      std::vector<uint8_t> t0;
-      const uint8_t* inf = nullptr;
-      if (d->b_g2_inf != nullptr) {
-        t0.assign((P.ma + 7) / 8 + 1, 0);
-        for (uint64_t i = 0; i < P.ma; i++)
-          if ((d->b_g2_inf[(lo + i) >> 3] >> ((lo + i) & 7)) & 1) t0[i >> 3] |= (uint8_t)(1u << (i & 7));
-        inf = t0.data();
-      }
-      stage_points<G2::Affine>(dpts.p, words, 0, d->b_g2_query + 24 * lo, inf, P.ma, st);
+      Picked g2_pts;
+      pick(g2_pts, d->b_g2_query, d->b_g2_inf, 0, P.ma, 0, 24);
+      stage_points<G2::Affine>(dpts.p, words, 0, g2_pts.pts, g2_pts.inf, P.ma, st);
       if (P.with_vk) {
         stage_points<G2::Affine>(dpts.p, words, P.ma, d->beta_g2, nullptr, 1, st);
         stage_points<G2::Affine>(dpts.p, words, (uint64_t)P.ma + 1, d->delta_g2, nullptr, 1, st);
@@ -577,12 +639,18 @@ b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from
   });
 }
 
+b2z_status b2z_pk_upload_slice(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t from, uint32_t to, uint32_t den,
+                               b2z_pk** out) {
+  return pk_upload_impl(ctx, d, from, to, den, 0, 0, out);
+}
+
 b2z_status b2z_pk_upload_shard(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t rank, uint32_t world, b2z_pk** out) {
   if (world < 1 || rank >= world) {
     if (out) *out = nullptr;
     return guarded(ctx, [&](Ctx&) { B2Z_REQUIRE(false, B2Z_EINVAL, "b2z_pk_upload_shard: need rank < world"); });
   }
-  return b2z_pk_upload_slice(ctx, d, rank, rank + 1, world, out);
+  // variables block-cyclic over the ranks (balanced for any witness), h positions in contiguous chunks
+  return pk_upload_impl(ctx, d, rank, rank + 1, world, rank, world > 1 ? world : 0, out);
 }
 
 b2z_status b2z_pk_upload(b2z_ctx* ctx, const b2z_pk_desc* d, b2z_pk** out) {

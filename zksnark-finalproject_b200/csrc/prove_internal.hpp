@@ -20,7 +20,7 @@ void prove_begin_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[
 void prove_begin_sorts_on(Ctx& c, const b2z_pk* pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4]);
 uint32_t pk_h_chunk(const b2z_pk* pk, uint32_t* h_lo);
 void prove_dist_h_sort_on(Ctx& c, const b2z_pk* pk, const FrEl* d_h, cudaStream_t st);
-void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t ready, uint8_t* partial_out);
+void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t wm_done, cudaStream_t h_st, uint8_t* partial_out);
 void combine_partials_host(const uint8_t* partials, uint32_t world, uint8_t proof_out[192]);
 // remembers where the "assignment uploaded" flag of the r1cs used by shard_begin lives; prove_finish_on clears it
 void pk_bind_assignment_flag(const b2z_pk* pk, bool* flag);

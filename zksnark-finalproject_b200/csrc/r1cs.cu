@@ -561,10 +561,10 @@ b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* d, const uint64_t* z, int z_is
     B2Z_CUDA(cudaStreamSynchronize(ws));
     dist_barrier(D, "witness-map step 3");
     wm_dist_step4(&c, nd, D.log_n, ws);
-    prove_dist_h_sort_on(c, D.pk, nd.y[0], ws);
     B2Z_CUDA(cudaEventRecord(D.ev_ready, ws));
+    prove_dist_h_sort_on(c, D.pk, nd.y[0], ws);           // hides under the z-only accumulations
     // ---- the five accumulations back to back, host epilogue of this shard
-    prove_dist_finish_on(c, D.pk, D.ev_ready, D.partials + (size_t)D.rank * kPartial);
+    prove_dist_finish_on(c, D.pk, D.ev_ready, ws, D.partials + (size_t)D.rank * kPartial);
     // ---- partial sums meet in the shared host memory; every rank combines
     dist_barrier(D, "the accumulations");
     combine_partials_host(D.partials, D.world, proof_out);
