@@ -20,15 +20,17 @@ b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
   ctx->impl.device = device_id;
   try {
     B2Z_CUDA(cudaSetDevice(device_id));
-    // The aux streams carry the z-only MSMs, whose sorts gate the first (GPU-filling) accumulation:
-    // they get the higher priority so that those sorts are not slowed by the witness map, which runs
-    // on the main stream and is only needed by the LAST accumulation (H) -- it has the whole heavy
-    // phase to finish in the room the G1 accumulations leave.
+    // Priorities.  The main stream carries the row evaluation, the witness map and the H sum -- the chain the
+    // LAST accumulation waits for -- and gets the highest priority: its integer-bound transform CTAs then take
+    // every SM slot a retiring sort CTA frees, so the (latency / atomics bound) sorts of the z-only MSMs on the
+    // auxiliary streams run beside the transforms instead of in front of them (the sorts' thousands of CTAs
+    // otherwise fill every thread slot first: 5 ms of a 2^22 proof with nothing else running).
     int prio_lo = 0, prio_hi = 0;
     B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_lo));
+    const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+    B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 4; i++)
-      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, prio_hi));
+      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, prio_mid));
   } catch (const StatusError& e) {
     delete ctx;
     return e.code;

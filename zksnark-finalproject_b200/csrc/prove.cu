@@ -120,6 +120,7 @@ struct PkImpl {
   cudaEvent_t ev_z = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_sorted[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_accum[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_wm = nullptr;       // witness-map transforms of the proof in flight are done (gates the first accumulation)
   ~PkImpl() {
     if (h_out) cudaFreeHost(h_out);
     if (h_planes) cudaFreeHost(h_planes);
@@ -130,6 +131,7 @@ struct PkImpl {
       if (e) cudaEventDestroy(e);
     for (auto& e : ev_accum)
       if (e) cudaEventDestroy(e);
+    if (ev_wm) cudaEventDestroy(ev_wm);
   }
 };
 
@@ -250,7 +252,7 @@ static_assert(kPartialBytes == B2Z_PARTIAL_BYTES, "header constant out of sync")
 // does the host epilogue.  The single-GPU prover runs them back to back; the sharded prover with a
 // distributed witness map (b2z_groth16_shard_*) lets the caller exchange the coset evaluations between
 // prove_begin and prove_quotient while the z-only accumulations are already running.
-void prove_accums(Ctx& c, PkImpl& pk);
+void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate = nullptr);
 void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const uint64_t s[4], bool with_accums = true) {
   cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
   // host-side scalars: r, s, -(r s) as canonical integers
@@ -286,8 +288,14 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
   if (with_accums) prove_accums(c, pk);
 }
 
-void prove_accums(Ctx& c, PkImpl& pk) {
+// gate: fired when the witness map's transforms are done.  An accumulation kernel fills every SM for its whole
+// duration (the G2 one takes all registers), so a transform queued beside it only runs in the gaps BETWEEN the
+// accumulations and the H sum then waits for it with an idle GPU (8.7 of 100 ms at 2^22 before this gate).  The light
+// phase -- sorts (latency / atomics bound) next to row evaluation and transforms (integer-pipe bound) -- overlaps
+// well instead, and the accumulations then run back to back with the H sort hidden under them.
+void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate) {
   cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
+  if (gate) B2Z_CUDA(cudaStreamWaitEvent(sB, gate, 0));
   G1::Xyzz* g1o = pk.g1_out.p;
   // ---- accumulations B -> A -> B1 -> L (-> H in prove_quotient), chained by events.
   // The G2 accumulation (255 registers: it fills every SM, nothing can be scheduled beside it) goes
@@ -326,6 +334,7 @@ void prove_h_finish(Ctx& c, PkImpl& pk, cudaStream_t st = nullptr) {
 void prove_quotient(Ctx& c, PkImpl& pk, FrEl* d_a, const FrEl* d_b, const FrEl* d_c, bool with_h_finish = true) {
   cudaStream_t st = c.stream;
   witness_map_quotient(&c, d_a, d_b, d_c, pk.log_n, /*natural_out=*/false, st);    // whole domain, every shard
+  B2Z_CUDA(cudaEventRecord(pk.ev_wm, st));
   fr_from_mont_device(&c, d_a + pk.h_lo, pk.hc.p, pk.hn, st);
   msm_sort<G1>(&c, 0, pk.h, pk.hc.p, pk.hn, nullptr, st);
   if (with_h_finish) prove_h_finish(c, pk);
@@ -359,7 +368,9 @@ void prove_partial_device(Ctx& c, PkImpl& pk, FrEl* d_a, FrEl* d_b, FrEl* d_c, c
   prove_begin(c, pk, d_z, r, s, /*with_accums=*/false);
   witness_map_transform3(&c, d_a, d_b, d_c, pk.log_n, c.stream);
   prove_quotient(c, pk, d_a, d_b, d_c, /*with_h_finish=*/false);
-  prove_accums(c, pk);
+  // small domains: the transforms run in 128-thread CTAs that fit on an SM beside a G1 accumulation and fill its
+  // idle issue slots (the accumulations are latency-bound there), so no gate
+  prove_accums(c, pk, pk.log_n >= 19 ? pk.ev_wm : nullptr);
   prove_h_finish(c, pk);
   prove_end(c, pk, partial_out);
 }
@@ -444,8 +455,7 @@ void prove_dist_h_sort_on(Ctx& c, const b2z_pk* pk, const FrEl* d_h, cudaStream_
 // the other accumulations; then the host epilogue
 void prove_dist_finish_on(Ctx& c, const b2z_pk* pk, cudaEvent_t wm_done, cudaStream_t h_st, uint8_t* partial_out) {
   PkImpl& P = pk_of(c, pk, "b2z_dist_prove");
-  B2Z_CUDA(cudaStreamWaitEvent(c.aux[1], wm_done, 0));    // the G2 accumulation opens the chain
-  prove_accums(c, P);
+  prove_accums(c, P, wm_done);                            // the G2 accumulation opens the chain
   prove_h_finish(c, P, h_st);
   prove_end(c, P, partial_out);
 }
@@ -635,6 +645,7 @@ static b2z_status pk_upload_impl(b2z_ctx* ctx, const b2z_pk_desc* d, uint32_t fr
     for (auto& e : P.ev_done) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : P.ev_sorted) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : P.ev_accum) B2Z_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    B2Z_CUDA(cudaEventCreateWithFlags(&P.ev_wm, cudaEventDisableTiming));
     *out = pk.release();
   });
 }

@@ -5,7 +5,9 @@
 // The matrices are static per circuit: uploaded once as CSR (row offsets, column indices,
 // Montgomery coefficients), then every proof sends only z (32 B per variable) instead of the
 // three evaluation vectors (96 B per domain point).  A gather-bound kernel: one thread per row.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "api_glue.hpp"
 #include "msm.hpp"
@@ -18,8 +20,23 @@ struct CsrDev {
   DevBuf<FrEl> coeffs;
 };
 
+// Two-pass row evaluation.  The rows of these circuits are wildly uneven (1 entry for a multiplication gate, up to
+// 33 for an inlined Poseidon MDS row; a warp of 32 consecutive rows does 3.3x the multiplications it needs when one
+// thread owns one row), so the multiplications are done per ENTRY (perfectly balanced; entries whose coefficient is
+// 1 -- every multiplication-gate row -- are plain copies, flagged in the column word) and only the cheap additions
+// per row.  `rows_out` outputs per matrix; the instance rows a[nc + j] = z[j] are ordinary one-entry rows of A.
+constexpr uint32_t kCoefOne = 0x80000000u;
+struct EvalPlan {
+  DevBuf<uint32_t> rp[3], ci[3];
+  DevBuf<FrEl> cf[3];
+  DevBuf<FrEl> prod;               // the three matrices' products back to back
+  uint32_t nnz[3] = {0, 0, 0};
+  uint32_t rows_out = 0;
+};
+
 struct R1csImpl {
   const Ctx* owner = nullptr;      // holds per-proof scratch (z, ea, eb, ec): belongs to the uploading context
+  EvalPlan plan;                   // all n rows, natural order
   uint64_t nc = 0, l = 0, m = 0;
   uint32_t log_n = 0;
   CsrDev mat[3];
@@ -42,27 +59,13 @@ __device__ __forceinline__ FrEl ldg32(const FrEl* p) {
   return r;
 }
 
-// grid.y selects the matrix; out[mat][row]
-__global__ void r1cs_eval_kernel(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ ci0,
-                                 const FrEl* __restrict__ cf0, const uint32_t* __restrict__ rp1,
-                                 const uint32_t* __restrict__ ci1, const FrEl* __restrict__ cf1,
-                                 const uint32_t* __restrict__ rp2, const uint32_t* __restrict__ ci2,
-                                 const FrEl* __restrict__ cf2, const FrEl* __restrict__ z, uint32_t nc, uint32_t l,
-                                 FrEl* a, FrEl* b, FrEl* c) {
-  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t which = blockIdx.y;
-  const uint32_t* rp = which == 0 ? rp0 : (which == 1 ? rp1 : rp2);
-  const uint32_t* ci = which == 0 ? ci0 : (which == 1 ? ci1 : ci2);
-  const FrEl* cf = which == 0 ? cf0 : (which == 1 ? cf1 : cf2);
-  FrEl* out = which == 0 ? a : (which == 1 ? b : c);
-  if (row < nc) {
-    FrEl acc = Fr::zero();
-    const uint32_t end = rp[row + 1];
-    for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, Fr::mul(ldg32(cf + k), ldg32(z + ci[k])));   // coeff canonical
-    out[row] = Fr::reduce(acc);
-  } else if (which == 0 && row < nc + l) {
-    out[row] = Fr::reduce(ldg32(z + (row - nc)));
-  }
+__device__ __forceinline__ FrEl ld32(const FrEl* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  const uint4 a = q[0], b = q[1];
+  FrEl r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+  r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+  return r;
 }
 
 // y = M x  for a CSR matrix over Fr (x, coefficients canonical Montgomery); one thread per row
@@ -76,32 +79,106 @@ __global__ void spmv_kernel(const uint32_t* __restrict__ rp, const uint32_t* __r
   y[row] = Fr::reduce(acc);
 }
 
-// Row evaluation for ONE RANK of the tile-sharded witness map: local index li of the column-owned layout is
-// the global row index with the rank inserted at bits [ob, ob + wbits); every local slot is written (zero
-// beyond the rows).  grid.y selects the matrix.
-__global__ void r1cs_eval_dist_kernel(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ ci0,
-                                      const FrEl* __restrict__ cf0, const uint32_t* __restrict__ rp1,
-                                      const uint32_t* __restrict__ ci1, const FrEl* __restrict__ cf1,
-                                      const uint32_t* __restrict__ rp2, const uint32_t* __restrict__ ci2,
-                                      const FrEl* __restrict__ cf2, const FrEl* __restrict__ z, uint32_t nc, uint32_t l,
-                                      uint32_t ob, uint32_t wbits, uint32_t me, uint32_t nl, FrEl* a, FrEl* b, FrEl* c) {
-  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-  if (li >= nl) return;
-  const uint32_t row = ((li >> ob) << (ob + wbits)) | (me << ob) | (li & ((1u << ob) - 1));
+__global__ void r1cs_products_kernel(const uint32_t* __restrict__ ci0, const FrEl* __restrict__ cf0, uint32_t n0,
+                                     const uint32_t* __restrict__ ci1, const FrEl* __restrict__ cf1, uint32_t n1,
+                                     const uint32_t* __restrict__ ci2, const FrEl* __restrict__ cf2, uint32_t n2,
+                                     const FrEl* __restrict__ z, FrEl* prod) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t which = blockIdx.y;
-  const uint32_t* rp = which == 0 ? rp0 : (which == 1 ? rp1 : rp2);
+  const uint32_t cnt = which == 0 ? n0 : (which == 1 ? n1 : n2);
+  if (k >= cnt) return;
   const uint32_t* ci = which == 0 ? ci0 : (which == 1 ? ci1 : ci2);
   const FrEl* cf = which == 0 ? cf0 : (which == 1 ? cf1 : cf2);
+  FrEl* out = prod + (which == 0 ? 0 : (which == 1 ? n0 : n0 + n1));
+  const uint32_t c = ci[k];
+  const FrEl zv = ldg32(z + (c & ~kCoefOne));
+  out[k] = (c & kCoefOne) ? zv : Fr::mul(ldg32(cf + k), zv);   // coefficient canonical, result lazy
+}
+
+__global__ void r1cs_rowsum_kernel(const uint32_t* __restrict__ rp0, const uint32_t* __restrict__ rp1,
+                                   const uint32_t* __restrict__ rp2, uint32_t n0, uint32_t n1,
+                                   const FrEl* __restrict__ prod, uint32_t rows, FrEl* a, FrEl* b, FrEl* c) {
+  const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const uint32_t which = blockIdx.y;
+  const uint32_t* rp = which == 0 ? rp0 : (which == 1 ? rp1 : rp2);
+  const FrEl* p = prod + (which == 0 ? 0 : (which == 1 ? n0 : n0 + n1));
   FrEl* out = which == 0 ? a : (which == 1 ? b : c);
   FrEl acc = Fr::zero();
-  if (row < nc) {
-    const uint32_t end = rp[row + 1];
-    for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, Fr::mul(ldg32(cf + k), ldg32(z + ci[k])));
-    acc = Fr::reduce(acc);
-  } else if (which == 0 && row < nc + l) {
-    acc = Fr::reduce(ldg32(z + (row - nc)));
+  const uint32_t end = rp[row + 1];
+  for (uint32_t k = rp[row]; k < end; k++) acc = Fr::add(acc, ld32(p + k));
+  out[row] = Fr::reduce(acc);
+}
+
+// Host CSR of one matrix (as uploaded) -> the plan's arrays for `rows_out` outputs, output row j being global row
+// row_of(j) (>= nc + extra: empty).  Matrix A carries the l instance rows after its nc constraint rows.
+struct HostCsr {
+  std::vector<uint32_t> rp, ci;
+  std::vector<FrEl> cf;
+};
+template <class RowOf>
+void plan_matrix(EvalPlan& P, int k, const HostCsr& M, uint64_t nc, uint64_t l, uint32_t rows_out, RowOf row_of,
+                 cudaStream_t st) {
+  const FrEl one = Fr::one();
+  std::vector<uint32_t> rp(rows_out + 1, 0), ci;
+  std::vector<FrEl> cf;
+  for (uint32_t j = 0; j < rows_out; j++) {
+    const uint64_t row = row_of(j);
+    if (row < nc) {
+      for (uint32_t e = M.rp[row]; e < M.rp[row + 1]; e++) {
+        const bool is_one = std::memcmp(M.cf[e].l, one.l, sizeof(one.l)) == 0;
+        ci.push_back(M.ci[e] | (is_one ? kCoefOne : 0u));
+        cf.push_back(M.cf[e]);
+      }
+    } else if (k == 0 && row < nc + l) {
+      ci.push_back((uint32_t)(row - nc) | kCoefOne);
+      cf.push_back(one);
+    }
+    rp[j + 1] = (uint32_t)ci.size();
   }
-  out[li] = acc;
+  P.nnz[k] = (uint32_t)ci.size();
+  P.rp[k].alloc(rp.size());
+  P.ci[k].alloc(ci.size() ? ci.size() : 1);
+  P.cf[k].alloc(cf.size() ? cf.size() : 1);
+  B2Z_CUDA(cudaMemcpyAsync(P.rp[k].p, rp.data(), rp.size() * 4, cudaMemcpyHostToDevice, st));
+  if (!ci.empty()) {
+    B2Z_CUDA(cudaMemcpyAsync(P.ci[k].p, ci.data(), ci.size() * 4, cudaMemcpyHostToDevice, st));
+    B2Z_CUDA(cudaMemcpyAsync(P.cf[k].p, cf.data(), cf.size() * sizeof(FrEl), cudaMemcpyHostToDevice, st));
+  }
+  B2Z_CUDA(cudaStreamSynchronize(st));   // the vectors are locals
+}
+void plan_finish(EvalPlan& P, uint32_t rows_out) {
+  P.rows_out = rows_out;
+  const size_t total = (size_t)P.nnz[0] + P.nnz[1] + P.nnz[2];
+  P.prod.alloc(total ? total : 1);
+}
+// device CSR -> host (dist set-up: the caller's arrays are gone by then)
+HostCsr download_csr(const CsrDev& d, uint64_t nc, cudaStream_t st) {
+  HostCsr h;
+  h.rp.resize(nc + 1);
+  B2Z_CUDA(cudaMemcpyAsync(h.rp.data(), d.row_ptr.p, (nc + 1) * 4, cudaMemcpyDeviceToHost, st));
+  B2Z_CUDA(cudaStreamSynchronize(st));
+  const size_t nnz = h.rp[nc];
+  h.ci.resize(nnz);
+  h.cf.resize(nnz);
+  if (nnz) {
+    B2Z_CUDA(cudaMemcpyAsync(h.ci.data(), d.cols.p, nnz * 4, cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaMemcpyAsync(h.cf.data(), d.coeffs.p, nnz * sizeof(FrEl), cudaMemcpyDeviceToHost, st));
+    B2Z_CUDA(cudaStreamSynchronize(st));
+  }
+  return h;
+}
+void run_plan(Ctx& c, const EvalPlan& P, const FrEl* d_z, FrEl* a, FrEl* b, FrEl* cc, cudaStream_t st) {
+  ProfileScope ps(&c, PH_R1CS_EVAL, st, 3ull * P.rows_out);
+  const uint32_t mx = std::max(P.nnz[0], std::max(P.nnz[1], P.nnz[2]));
+  if (mx) {
+    r1cs_products_kernel<<<dim3((mx + 255) / 256, 3), 256, 0, st>>>(P.ci[0].p, P.cf[0].p, P.nnz[0], P.ci[1].p, P.cf[1].p,
+                                                                   P.nnz[1], P.ci[2].p, P.cf[2].p, P.nnz[2], d_z, P.prod.p);
+    B2Z_LAUNCHED(&c);
+  }
+  r1cs_rowsum_kernel<<<dim3((P.rows_out + 255) / 256, 3), 256, 0, st>>>(P.rp[0].p, P.rp[1].p, P.rp[2].p, P.nnz[0], P.nnz[1],
+                                                                       P.prod.p, P.rows_out, a, b, cc);
+  B2Z_LAUNCHED(&c);
 }
 
 void upload_csr(CsrDev& d, const uint64_t* row_ptr, const uint32_t* cols, const uint64_t* coeffs, uint64_t nc,
@@ -128,17 +205,7 @@ void upload_csr(CsrDev& d, const uint64_t* row_ptr, const uint32_t* cols, const 
 }
 
 void eval_rows(Ctx& c, R1csImpl& R, const FrEl* d_z, FrEl* a, FrEl* b, FrEl* cc, cudaStream_t st) {
-  const size_t n = (size_t)1 << R.log_n;
-  ProfileScope ps(&c, PH_R1CS_EVAL, st, 3 * (R.nc + R.l));
-  B2Z_CUDA(cudaMemsetAsync(a, 0, n * sizeof(FrEl), st));
-  B2Z_CUDA(cudaMemsetAsync(b, 0, n * sizeof(FrEl), st));
-  B2Z_CUDA(cudaMemsetAsync(cc, 0, n * sizeof(FrEl), st));
-  const uint32_t rows = (uint32_t)(R.nc + R.l);
-  const dim3 grid((rows + 127) / 128, 3);
-  r1cs_eval_kernel<<<grid, 128, 0, st>>>(R.mat[0].row_ptr.p, R.mat[0].cols.p, R.mat[0].coeffs.p, R.mat[1].row_ptr.p,
-                                         R.mat[1].cols.p, R.mat[1].coeffs.p, R.mat[2].row_ptr.p, R.mat[2].cols.p,
-                                         R.mat[2].coeffs.p, d_z, (uint32_t)R.nc, (uint32_t)R.l, a, b, cc);
-  B2Z_LAUNCHED(&c);
+  run_plan(c, R.plan, d_z, a, b, cc, st);
 }
 
 // rows of ONE matrix (0 = A with the instance rows appended, 1 = B, 2 = C) against z, zero-padded to the domain
@@ -200,6 +267,23 @@ b2z_status b2z_r1cs_upload(b2z_ctx* ctx, uint64_t num_constraints, uint64_t num_
     upload_csr(R.mat[1], b_row_ptr, b_cols, b_coeffs, num_constraints, num_variables, c.stream);
     upload_csr(R.mat[2], c_row_ptr, c_cols, c_coeffs, num_constraints, num_variables, c.stream);
     const size_t n = (size_t)1 << log_n;
+    {
+      const uint64_t* rps[3] = {a_row_ptr, b_row_ptr, c_row_ptr};
+      const uint32_t* cis[3] = {a_cols, b_cols, c_cols};
+      const uint64_t* cfs[3] = {a_coeffs, b_coeffs, c_coeffs};
+      for (int k = 0; k < 3; k++) {
+        HostCsr h;
+        const uint64_t nnz = rps[k][num_constraints];
+        h.rp.resize(num_constraints + 1);
+        for (uint64_t i = 0; i <= num_constraints; i++) h.rp[i] = (uint32_t)rps[k][i];
+        h.ci.assign(cis[k], cis[k] + nnz);
+        h.cf.resize(nnz);
+        if (nnz) std::memcpy(h.cf.data(), cfs[k], nnz * sizeof(FrEl));
+        plan_matrix(R.plan, k, h, num_constraints, num_instance, (uint32_t)n, [](uint32_t j) { return (uint64_t)j; },
+                    c.stream);
+      }
+      plan_finish(R.plan, (uint32_t)n);
+    }
     R.z.alloc(num_variables); R.ea.alloc(n); R.eb.alloc(n); R.ec.alloc(n);
     B2Z_CUDA(cudaEventCreateWithFlags(&R.ev_z, cudaEventDisableTiming));
     *out = r.release();
@@ -374,6 +458,7 @@ struct DistImpl {
   cudaStream_t wm_st = nullptr;
   cudaEvent_t ev_ready = nullptr;
   NttDist nd;
+  EvalPlan plan;                          // this rank's rows of the column-owned layout, local order
   ~DistImpl() {
     for (uint32_t p = 0; p < 8; p++)
       if (peer_ipc[p] && peer_region[p]) cudaIpcCloseMemHandle(peer_region[p]);
@@ -446,6 +531,19 @@ b2z_status b2z_dist_create(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, uint32_t
     B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     B2Z_CUDA(cudaStreamCreateWithPriority(&D.wm_st, cudaStreamNonBlocking, hi));
     B2Z_CUDA(cudaEventCreateWithFlags(&D.ev_ready, cudaEventDisableTiming));
+    // this rank's rows: local index li of the column-owned layout = global row with the rank inserted at the
+    // ownership bits
+    {
+      const uint32_t ob = ntt_dist_col_bits(R.log_n, wbits);
+      auto row_of = [=](uint32_t li) {
+        return (uint64_t)(((li >> ob) << (ob + wbits)) | (rank << ob) | (li & ((1u << ob) - 1)));
+      };
+      for (int k = 0; k < 3; k++) {
+        const HostCsr h = download_csr(R.mat[k], R.nc, D.wm_st);
+        plan_matrix(D.plan, k, h, R.nc, R.l, (uint32_t)D.nl, row_of, D.wm_st);
+      }
+      plan_finish(D.plan, (uint32_t)D.nl);
+    }
     // warm the twiddle tables now: they are built lazily on first use
     for (TwKind k : {TW_INV, TW_COSET_FWD, TW_COSET_INV}) ntt_twiddles(&c, R.log_n, k, D.wm_st);
     B2Z_CUDA(cudaStreamSynchronize(D.wm_st));
@@ -541,16 +639,7 @@ b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* d, const uint64_t* z, int z_is
         nd.peer_y[v][p] = reinterpret_cast<FrEl*>(D.vec_of(D.peer_region[p], 1, v));
       }
     }
-    {
-      ProfileScope ps(&c, PH_R1CS_EVAL, ws, 3 * D.nl);
-      const dim3 grid((uint32_t)((D.nl + 127) / 128), 3);
-      r1cs_eval_dist_kernel<<<grid, 128, 0, ws>>>(R.mat[0].row_ptr.p, R.mat[0].cols.p, R.mat[0].coeffs.p, R.mat[1].row_ptr.p,
-                                                 R.mat[1].cols.p, R.mat[1].coeffs.p, R.mat[2].row_ptr.p, R.mat[2].cols.p,
-                                                 R.mat[2].coeffs.p, D.z(), (uint32_t)R.nc, (uint32_t)R.l,
-                                                 ntt_dist_col_bits(D.log_n, D.wbits), D.wbits, D.rank, (uint32_t)D.nl, nd.x[0],
-                                                 nd.x[1], nd.x[2]);
-      B2Z_LAUNCHED(&c);
-    }
+    run_plan(c, D.plan, D.z(), nd.x[0], nd.x[1], nd.x[2], ws);
     wm_dist_step1(&c, nd, D.log_n, ws);
     B2Z_CUDA(cudaStreamSynchronize(ws));
     dist_barrier(D, "witness-map step 1");
