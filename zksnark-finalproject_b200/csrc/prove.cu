@@ -306,9 +306,10 @@ void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate) {
   // by the HOST (prove_end) while the GPU is still busy with L and H.  (With the scalar multiplications
   // on the GPU -- 1.5 ms each even with lane-cooperative arithmetic -- every order tried put one of them
   // on the critical path: 7.65-8.3 ms per C2 proof.)
-  // Chaining only pays when an accumulation fills the GPU: below ~64 k point references it is a few blocks
-  // and the chain would just add its kernels' latencies (Fibonacci: 5 variables) -- those run concurrently.
-  auto big = [](uint64_t n, uint32_t windows) { return n * windows >= (1u << 16); };
+  // Chaining only pays when an accumulation fills the GPU (148 SMs x 256 threads x >= 8 references each): below
+  // ~256 k point references a kernel is latency-bound with idle SM slots, and the chain would just add the
+  // kernels' latencies (Fibonacci: 5 variables; an eighth of the 16x16 matrix circuit) -- those run concurrently.
+  auto big = [](uint64_t n, uint32_t windows) { return n * windows >= (1u << 18); };
   const bool chain = big(pk.g2.n, pk.g2.windows) || big(pk.a_set.n, pk.a_set.windows);
   if (chain) {
     B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
@@ -327,7 +328,7 @@ void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate) {
 
 // d_a, d_b, d_c: evaluations of the three QAP combinations on the coset g H (d_a is clobbered)
 void prove_h_finish(Ctx& c, PkImpl& pk, cudaStream_t st = nullptr) {
-  const bool chain = (uint64_t)pk.h.n * pk.h.windows >= (1u << 16);
+  const bool chain = (uint64_t)pk.h.n * pk.h.windows >= (1u << 18);
   pk.h_stream = st ? st : c.stream;
   msm_finish<G1>(&c, 0, pk.h, pk.g1_out.p + 4, pk.h_stream, chain ? pk.ev_accum[2] : nullptr, nullptr, &pk.hp[4]);
 }
