@@ -346,6 +346,7 @@ class Bench:
         for _ in range(warmup):
             step_value()
         launches0 = L.b2z_kernel_launches(ctx.handle)
+        log("library kernels launched before the timed region: %d" % launches0)
         L.b2z_profile_enable(ctx.handle, 1)
         clocks = ClockSampler(self.local_rank)
         clocks.start()

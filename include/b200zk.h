@@ -157,8 +157,10 @@ B2Z_API b2z_status b2z_groth16_prove_r1cs(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1
 
 /* ---- point-sharded proving across the GPUs of one box ------------------------------------
  * An MSM is a sum over independent (scalar, point) pairs, so a proof shards by points
- * (SURVEY.md 8(e)): rank k of `world` keeps variables [m k/world, m (k+1)/world) of the
- * a / b_g1 / b_g2 / l queries and the same fraction of the (bit-reversed) h bases; rank 0 also
+ * (SURVEY.md 8(e)): rank k of `world` keeps, of the a / b_g1 / b_g2 / l queries, the variables of
+ * blocks k, k + world, k + 2 world, ... (blocks of 64 variables: Groth16 assignments have long stretches
+ * of small / Boolean values, and contiguous ranges left some GPUs with a third of the others' work), and
+ * the contiguous chunk [n k/world, n (k+1)/world) of the (bit-reversed) h bases; rank 0 also
  * keeps the alpha/beta/delta terms.  Every rank passes the SAME full desc and the same full
  * a/b/c/z/r/s; the witness map runs on every rank.  Each rank gets B2Z_PARTIAL_BYTES of partial
  * sums (XYZZ limbs: A | s*A | r*B1 | L | H in G1, B in G2 -- scalar multiplication is linear, so
@@ -301,6 +303,11 @@ B2Z_API b2z_status b2z_dist_export(b2z_ctx* ctx, b2z_dist* dist, uint8_t ipc_han
 /* make rank `peer`'s region reachable: exactly one of ipc_handle (other process) / device_ptr (same process) */
 B2Z_API b2z_status b2z_dist_attach(b2z_ctx* ctx, b2z_dist* dist, uint32_t peer, const uint8_t* ipc_handle,
                                    void* device_ptr);
+/* host only (no GPU, no ctx): the last step of b2z_dist_prove on its own -- this rank's B2Z_PARTIAL_BYTES go into
+ * the shared buffer, a barrier, every rank combines all `world` partials into the proof, a second barrier.
+ * *epoch: this rank's barrier counter (start at 0; same call sequence on every rank).                          */
+B2Z_API b2z_status b2z_dist_combine_shared(void* shared_host, uint32_t rank, uint32_t world, uint32_t* epoch,
+                                           const uint8_t* my_partial, uint8_t proof_out[192]);
 B2Z_API b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* dist, const uint64_t* z, int z_is_full_device_copy,
                                   const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[192]);
 

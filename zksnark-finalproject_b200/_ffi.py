@@ -73,6 +73,8 @@ SIGNATURES = {
     "b2z_groth16_verify_with_processed_vk": (ctypes.c_int32, [vp, ctypes.c_uint64, vp, ctypes.c_uint64, vp,
                                                                ctypes.POINTER(ctypes.c_int32)]),
     "b2z_dist_shared_bytes": (ctypes.c_uint64, [ctypes.c_uint32]),
+    "b2z_dist_combine_shared": (ctypes.c_int32, [vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), vp,
+                                                  vp]),
     "b2z_dist_create": (ctypes.c_int32, [vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32, vp, ctypes.POINTER(vp)]),
     "b2z_dist_destroy": (None, [vp, vp]),
     "b2z_dist_export": (ctypes.c_int32, [vp, vp, vp, ctypes.POINTER(vp)]),

@@ -484,20 +484,36 @@ struct DistImpl {
   }
 };
 namespace {
-void dist_barrier(DistImpl& D, const char* where) {
-  D.epoch++;
-  __atomic_store_n(D.flags + D.rank * kFlagStride, D.epoch, __ATOMIC_RELEASE);
+// host barrier of the ranks on the shared flag words; false = a peer never arrived
+bool shared_barrier(uint32_t* flags, uint32_t rank, uint32_t world, uint32_t* epoch) {
+  const uint32_t e = ++*epoch;
+  __atomic_store_n(flags + rank * kFlagStride, e, __ATOMIC_RELEASE);
   uint64_t spins = 0;
-  for (uint32_t p = 0; p < D.world; p++) {
+  for (uint32_t p = 0; p < world; p++) {
     // wrap-safe: the peer's epoch has reached ours
-    while ((int32_t)(__atomic_load_n(D.flags + p * kFlagStride, __ATOMIC_ACQUIRE) - D.epoch) < 0) {
+    while ((int32_t)(__atomic_load_n(flags + p * kFlagStride, __ATOMIC_ACQUIRE) - e) < 0) {
 #if defined(__x86_64__)
       __builtin_ia32_pause();
 #endif
-      if (++spins > (1ull << 33))
-        throw StatusError{B2Z_ECUDA, std::string("b2z_dist_prove: a peer rank did not reach the barrier after ") + where};
+      if (++spins > (1ull << 33)) return false;
     }
   }
+  return true;
+}
+void dist_barrier(DistImpl& D, const char* where) {
+  if (!shared_barrier(D.flags, D.rank, D.world, &D.epoch))
+    throw StatusError{B2Z_ECUDA, std::string("b2z_dist_prove: a peer rank did not reach the barrier after ") + where};
+}
+// the last step of a distributed proof: partial sums meet in the shared buffer, every rank combines; the second
+// barrier keeps a fast rank from overwriting its slot (next proof) before everybody has read it
+bool shared_combine(void* shared_host, uint32_t rank, uint32_t world, uint32_t* epoch, const uint8_t* my_partial,
+                    uint8_t proof_out[192]) {
+  uint32_t* flags = static_cast<uint32_t*>(shared_host);
+  uint8_t* partials = static_cast<uint8_t*>(shared_host) + (size_t)world * kFlagStride * 4;
+  if (my_partial != partials + (size_t)rank * kPartial) std::memcpy(partials + (size_t)rank * kPartial, my_partial, kPartial);
+  if (!shared_barrier(flags, rank, world, epoch)) return false;
+  combine_partials_host(partials, world, proof_out);
+  return shared_barrier(flags, rank, world, epoch);
 }
 }  // namespace
 }  // namespace b2z
@@ -509,6 +525,12 @@ struct b2z_dist {
 extern "C" {
 
 uint64_t b2z_dist_shared_bytes(uint32_t world) { return (uint64_t)world * (kFlagStride * 4 + kPartial); }
+
+b2z_status b2z_dist_combine_shared(void* shared_host, uint32_t rank, uint32_t world, uint32_t* epoch,
+                                   const uint8_t* my_partial, uint8_t proof_out[192]) {
+  if (!shared_host || !epoch || !my_partial || !proof_out || world == 0 || rank >= world) return B2Z_EINVAL;
+  return shared_combine(shared_host, rank, world, epoch, my_partial, proof_out) ? B2Z_OK : B2Z_ECUDA;
+}
 
 b2z_status b2z_dist_create(b2z_ctx* ctx, const b2z_pk* pk, b2z_r1cs* r, uint32_t rank, uint32_t world, void* shared_host,
                            b2z_dist** out) {
@@ -671,10 +693,8 @@ b2z_status b2z_dist_prove(b2z_ctx* ctx, b2z_dist* d, const uint64_t* z, int z_is
     // ---- the five accumulations back to back, host epilogue of this shard
     prove_dist_finish_on(c, D.pk, D.ev_ready, ws, D.partials + (size_t)D.rank * kPartial);
     // ---- partial sums meet in the shared host memory; every rank combines
-    dist_barrier(D, "the accumulations");
-    combine_partials_host(D.partials, D.world, proof_out);
-    // nobody may overwrite its partial (next proof) before every rank has combined
-    dist_barrier(D, "the combine");
+    if (!shared_combine(D.flags, D.rank, D.world, &D.epoch, D.partials + (size_t)D.rank * kPartial, proof_out))
+      throw StatusError{B2Z_ECUDA, "b2z_dist_prove: a peer rank did not reach the barrier after the accumulations"};
   });
 }
 
