@@ -48,9 +48,11 @@ void b2z_ctx_destroy(b2z_ctx* ctx) {
   for (auto& sp : ctx->impl.spans) {
     cudaEventDestroy(sp.start);
     cudaEventDestroy(sp.stop);
-    if (sp.units_pinned) cudaFreeHost(sp.units_pinned);
   }
   ctx->impl.spans.clear();
+  for (auto& e : ctx->impl.event_pool) cudaEventDestroy(e);
+  ctx->impl.event_pool.clear();
+  if (ctx->impl.units_pool) cudaFreeHost(ctx->impl.units_pool);
   if (ctx->impl.stream) cudaStreamDestroy(ctx->impl.stream);
   for (auto& s : ctx->impl.aux)
     if (s) cudaStreamDestroy(s);
@@ -58,7 +60,18 @@ void b2z_ctx_destroy(b2z_ctx* ctx) {
 }
 
 b2z_status b2z_profile_enable(b2z_ctx* ctx, int on) {
-  return guarded(ctx, [&](Ctx& c) { c.profile = on != 0; });
+  return guarded(ctx, [&](Ctx& c) {
+    if (on && c.units_pool == nullptr) {
+      // everything the spans need is created here, outside any timed region
+      B2Z_CUDA(cudaMallocHost(&c.units_pool, kUnitsPool * sizeof(uint32_t)));
+      for (int i = 0; i < 2048; i++) {
+        cudaEvent_t e;
+        B2Z_CUDA(cudaEventCreate(&e));
+        c.event_pool.push_back(e);
+      }
+    }
+    c.profile = on != 0;
+  });
 }
 
 b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset) {
@@ -76,11 +89,11 @@ b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64
     }
     if (reset) {
       for (auto& sp : c.spans) {
-        cudaEventDestroy(sp.start);
-        cudaEventDestroy(sp.stop);
-        if (sp.units_pinned) cudaFreeHost(sp.units_pinned);
+        c.event_pool.push_back(sp.start);
+        c.event_pool.push_back(sp.stop);
       }
       c.spans.clear();
+      c.units_used = 0;
     }
   });
 }

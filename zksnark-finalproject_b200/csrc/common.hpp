@@ -91,6 +91,7 @@ enum Phase {
   PH_COUNT = 8
 };
 
+constexpr uint32_t kUnitsPool = 4096;
 struct ProfileSpan {
   int phase;
   cudaEvent_t start, stop;
@@ -169,6 +170,11 @@ struct Ctx {
   bool ntt_attr_set[6] = {false, false, false, false, false, false};
   bool profile = false;
   std::vector<ProfileSpan> spans;
+  // pools, so that an enabled profiler costs the launching thread two event records per span and nothing else
+  // (creating events and page-locked words inside the timed region delayed the launches by milliseconds)
+  std::vector<cudaEvent_t> event_pool;
+  uint32_t* units_pool = nullptr;      // page-locked, kUnitsPool words
+  uint32_t units_used = 0;
   std::mutex span_mu;                  // spans are appended from the single calling thread; guards reads
   uint64_t launches = 0;               // kernels launched through this context
   void* msm_scratch = nullptr;         // MsmScratch arenas (msm.cu)

@@ -36,6 +36,40 @@ struct alignas(16) Fp {
 
 namespace detail {
 
+// Modulus limb as the multiplier of the reduction step's multiply-adds.  For Fr the limbs come from the constant
+// bank on the device instead of being immediates: ptxas splits a wide multiply-add whose multiplier is a 32-bit
+// immediate and whose destination pair differs from its addend pair into IMAD.X + IMAD.HI.U32.X (two trips through
+// the multiplier; half of all multiply-adds of the transform kernels in round 1's SASS), while a constant-bank
+// operand keeps the single IMAD.WIDE.U32.X.  (Fq's rows are allocated in place and fuse as they are.)
+#if defined(__CUDACC__)
+static __constant__ uint32_t kFrModulusLimbs[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+#endif
+template <class P>
+B2Z_HD uint32_t mod_limb(int j) { return P::p(j); }
+template <>
+B2Z_HD uint32_t mod_limb<FrParams>(int j) {
+#if defined(__CUDA_ARCH__)
+  return kFrModulusLimbs[j];
+#else
+  return FrParams::p(j);
+#endif
+}
+
+template <class P>
+B2Z_HD uint32_t mont_inv() { return P::INV; }
+#if defined(__CUDACC__)
+static __constant__ uint32_t kFrInv = 0xffffffffu;
+#endif
+template <>
+B2Z_HD uint32_t mont_inv<FrParams>() {
+#if defined(__CUDA_ARCH__)
+  return kFrInv;
+#else
+  return FrParams::INV;
+#endif
+}
+
 // One row of the product: acc += a * bi ; acc += m * p ; (acc's low limb is 0).
 // On entry (unless FIRST) E holds the previous row's O and O the previous row's E.
 template <class P, bool FIRST>
@@ -65,14 +99,14 @@ B2Z_HD void mont_row(uint32_t (&E)[P::N], uint32_t (&O)[P::N], const uint32_t (&
     for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(cf, E[j], E[j + 1], a[j], bi);
     O[N - 1] += ptx::addc(cf, 0u, 0u);
   }
-  const uint32_t m = E[0] * P::INV;
-  ptx::mad_wide_cc(cf, E[0], E[1], m, P::p(0));
+  const uint32_t m = E[0] * mont_inv<P>();
+  ptx::mad_wide_cc(cf, E[0], E[1], m, mod_limb<P>(0));
 #pragma unroll
-  for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(cf, E[j], E[j + 1], m, P::p(j));
+  for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(cf, E[j], E[j + 1], m, mod_limb<P>(j));
   const uint32_t c = ptx::addc(cf, 0u, 0u);
-  ptx::mad_wide_cc(cf, O[0], O[1], m, P::p(1));
+  ptx::mad_wide_cc(cf, O[0], O[1], m, mod_limb<P>(1));
 #pragma unroll
-  for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(cf, O[j], O[j + 1], m, P::p(j + 1));
+  for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(cf, O[j], O[j + 1], m, mod_limb<P>(j + 1));
   O[N - 1] += c;
 }
 

@@ -657,10 +657,14 @@ ProfileScope::ProfileScope(Ctx* c, int phase, cudaStream_t s, uint64_t units, co
   sp.phase = phase;
   sp.units = units;
   sp.units_pinned = nullptr;
-  B2Z_CUDA(cudaEventCreate(&sp.start));
-  B2Z_CUDA(cudaEventCreate(&sp.stop));
-  if (d_units != nullptr) {
-    B2Z_CUDA(cudaMallocHost(&sp.units_pinned, sizeof(uint32_t)));
+  auto take_event = [&](cudaEvent_t* e) {
+    if (!c->event_pool.empty()) { *e = c->event_pool.back(); c->event_pool.pop_back(); }
+    else B2Z_CUDA(cudaEventCreate(e));
+  };
+  take_event(&sp.start);
+  take_event(&sp.stop);
+  if (d_units != nullptr && c->units_pool != nullptr && c->units_used < kUnitsPool) {
+    sp.units_pinned = c->units_pool + c->units_used++;
     *sp.units_pinned = 0;
     // the count is produced by an earlier kernel on the same stream
     B2Z_CUDA(cudaMemcpyAsync(sp.units_pinned, d_units, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
