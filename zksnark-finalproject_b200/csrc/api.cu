@@ -27,10 +27,14 @@ b2z_status b2z_ctx_create(int device_id, b2z_ctx** out) {
     // otherwise fill every thread slot first: 5 ms of a 2^22 proof with nothing else running).
     int prio_lo = 0, prio_hi = 0;
     B2Z_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-    const int prio_mid = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+    // The auxiliary streams carry the z-only MSMs; their accumulations are chained A (aux 0) -> B1 (aux 2) -> B
+    // (aux 1) -> L (aux 3), and the sorts get the priorities that make them finish in that order.
+    auto below = [&](int p) { return p < prio_lo ? p + 1 : p; };
+    const int p1 = below(prio_hi), p2 = below(p1), p3 = below(p2);
+    const int aux_prio[4] = {p1, p3, p2, p3};
     B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 4; i++)
-      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, prio_mid));
+      B2Z_CUDA(cudaStreamCreateWithPriority(&ctx->impl.aux[i], cudaStreamNonBlocking, aux_prio[i]));
   } catch (const StatusError& e) {
     delete ctx;
     return e.code;

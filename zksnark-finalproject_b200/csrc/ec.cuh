@@ -125,6 +125,35 @@ struct Curve {
     return o;
   }
 
+  // The same for the accumulation hot loop: the (rare) P + P branch re-reads the base from `src` inside an out-of-line
+  // function instead of passing `q` by reference -- a by-reference argument makes the compiler park q in local
+  // memory on EVERY iteration (6 / 12 STL.128 per mixed addition in round 1's SASS), whether the branch is taken or not.
+  static B2Z_HD_NOINLINE Xyzz dbl_affine_at(const Affine* src, bool negated) {
+    Affine p = *src;
+    if (negated) p = neg(p);
+    return dbl_affine_inl(p);
+  }
+  static B2Z_HD Xyzz madd_inl_at(const Xyzz& a, const Affine& q, const Affine* src, bool negated) {
+    if (is_identity(a)) return from_affine(q);
+    const El u2 = F::mul(q.x, a.zz);
+    const El s2 = F::mul(q.y, a.zzz);
+    const El p = F::sub(u2, a.x);
+    const El r = F::sub(s2, a.y);
+    if (F::is_zero(p)) {
+      if (F::is_zero(r)) return dbl_affine_at(src, negated);
+      return identity();
+    }
+    const El pp = F::sqr(p);
+    const El ppp = F::mul(p, pp);
+    const El q1 = F::mul(a.x, pp);
+    Xyzz o;
+    o.x = F::sub(F::sub(F::sqr(r), ppp), F::dbl(q1));
+    o.y = F::sub(F::mul(r, F::sub(q1, o.x)), F::mul(a.y, ppp));
+    o.zz = F::mul(a.zz, pp);
+    o.zzz = F::mul(a.zzz, ppp);
+    return o;
+  }
+
   // general addition, 12M + 2S
   static B2Z_HD Xyzz add_inl(const Xyzz& a, const Xyzz& b) {
     if (is_identity(a)) return b;

@@ -295,13 +295,10 @@ void prove_begin(Ctx& c, PkImpl& pk, const FrEl* d_z, const uint64_t r[4], const
 // well instead, and the accumulations then run back to back with the H sort hidden under them.
 void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate) {
   cudaStream_t sA = c.aux[0], sB = c.aux[1], sB1 = c.aux[2], sL = c.aux[3];
-  if (gate) B2Z_CUDA(cudaStreamWaitEvent(sB, gate, 0));
   G1::Xyzz* g1o = pk.g1_out.p;
-  // ---- accumulations B -> A -> B1 -> L (-> H in prove_quotient), chained by events.
-  // The G2 accumulation (255 registers: it fills every SM, nothing can be scheduled beside it) goes
-  // first, right after the z-only sorts, so that its tail -- the longest -- hides under the G1
-  // accumulations.  A G1 accumulation leaves room on every SM for sort / NTT / tail blocks (the tail
-  // kernels are register-capped for exactly that), so the witness map and the other tails overlap too.
+  // ---- accumulations chained by events (order below).  Each accumulation kernel is sized to fill the GPU by
+  // itself; the G2 one (255 registers) leaves room for nothing, a G1 one leaves room on every SM for sort /
+  // transform / tail blocks (the tail kernels are register-capped for exactly that), so tails overlap the next sums.
   // Every reduction stops at its bit-plane sums; the serial Horner pass over them, s*A and r*B1 are done
   // by the HOST (prove_end) while the GPU is still busy with L and H.  (With the scalar multiplications
   // on the GPU -- 1.5 ms each even with lane-cooperative arithmetic -- every order tried put one of them
@@ -311,18 +308,23 @@ void prove_accums(Ctx& c, PkImpl& pk, cudaEvent_t gate) {
   // kernels' latencies (Fibonacci: 5 variables; an eighth of the 16x16 matrix circuit) -- those run concurrently.
   auto big = [](uint64_t n, uint32_t windows) { return n * windows >= (1u << 18); };
   const bool chain = big(pk.g2.n, pk.g2.windows) || big(pk.a_set.n, pk.a_set.windows);
-  if (chain) {
-    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[0], 0));
-    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[2], 0));
-    B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));
-  }
-  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, nullptr, pk.ev_accum[3], &pk.hp[1]);
-  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
-  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, chain ? pk.ev_accum[3] : nullptr, pk.ev_accum[0], &pk.hp[0]);
+  // Order A -> B1 -> B (G2) -> L (-> H).  Two G1 sums open the chain because a G1 accumulation leaves a quarter of
+  // every SM's registers free: the sorts of the other z-only MSMs (atomics-bound, starved while the transforms ran)
+  // finish BESIDE them instead of in front of the G2 accumulation, which takes every register of every SM.  The
+  // streams' priorities (api.cu) make the sorts finish in the order their sums need them.
+  if (gate) B2Z_CUDA(cudaStreamWaitEvent(sA, gate, 0));
+  msm_finish<G1>(&c, 1, pk.a_set, g1o + 0, sA, nullptr, pk.ev_accum[0], &pk.hp[0]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[0], sA));
+  if (!chain && gate) {
+    B2Z_CUDA(cudaStreamWaitEvent(sB1, gate, 0));
+    B2Z_CUDA(cudaStreamWaitEvent(sB, gate, 0));
+  }
   msm_finish<G1>(&c, 3, pk.b1_set, g1o + 5, sB1, chain ? pk.ev_accum[0] : nullptr, pk.ev_accum[1], &pk.hp[2]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[2], sB1));
-  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, chain ? pk.ev_accum[1] : nullptr, pk.ev_accum[2], &pk.hp[3]);
+  if (chain) B2Z_CUDA(cudaStreamWaitEvent(sB, pk.ev_sorted[3], 0));     // nothing runs beside the G2 sum: L's sort first
+  msm_finish<G2>(&c, 2, pk.g2, pk.g2_out.p, sB, chain ? pk.ev_accum[1] : nullptr, pk.ev_accum[3], &pk.hp[1]);
+  B2Z_CUDA(cudaEventRecord(pk.ev_done[1], sB));
+  msm_finish<G1>(&c, 4, pk.l_set, g1o + 3, sL, chain ? pk.ev_accum[3] : nullptr, pk.ev_accum[2], &pk.hp[3]);
   B2Z_CUDA(cudaEventRecord(pk.ev_done[3], sL));
 }
 
