@@ -12,13 +12,13 @@ KREGEX='regex:msm_|ntt_|wm_|fr_from_mont|canonicalize|scan_|bitrev|pack_flags|fb
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s $SKIP -c 90 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
-# accumulation launches per proof, in issue order: B (G2), A, B1, L, H (G1); 2 check proofs + 3 warm-up proofs = 25 launches
-# -> index 25 = B (G2), 26 = A (G1) of the first timed proof.  Transform passes: 5 per proof -> 25 = first pass (three
+# accumulation launches per proof, in issue order: A, B1 (G1), B (G2), L, H (G1); 2 check proofs + 3 warm-up proofs = 25 launches
+# -> index 25 = A (G1), 27 = B (G2) of the first timed proof.  Transform passes: 5 per proof -> 25 = first pass (three
 # vectors, high bits), 26 = the fused low pass.
-ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 26 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 25 -c 1 \
     -o gpurun_out/prof_accum_g1 $CMD > gpurun_out/ncu_full_accum_g1.log 2>&1
 echo "full accum g1 exit $?"
-ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 25 -c 1 \
+ncu --set full --clock-control none --import-source on -k regex:msm_accum_kernel -s 27 -c 1 \
     -o gpurun_out/prof_accum_g2 $CMD > gpurun_out/ncu_full_accum_g2.log 2>&1
 echo "full accum g2 exit $?"
 ncu --set full --clock-control none --import-source on -k regex:ntt_pass_kernel -s 25 -c 2 \
