@@ -323,6 +323,18 @@ B2Z_API b2z_status b2z_host_unregister(b2z_ctx* ctx, void* ptr);
  * suite check them against the oracle.  op: 0 mul, 1 add, 2 sub, 3 canonical form,
  * 4 inverse.  field: 0 = Fr (8 x u32), 1 = Fq (12 x u32); operands lazy (< 2p).      */
 B2Z_API int b2z_host_field_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* Fq inversion by division steps (csrc/inv_gcd.cuh, the shared inversion of the batched-affine bucket accumulation):
+ * a, out = 12 x u32 Montgomery limbs (a lazy, out canonical; 0 -> 0); returns the number of 30-step batches used. */
+B2Z_API int b2z_host_fq_inv_gcd(const uint32_t* a, uint32_t* out);
+/* The batched-affine bucket accumulation (csrc/accum_affine.cuh) run on the host, one emulated thread per segment:
+ * points = affine bases (24 / 48 u32 each), sorted = point references ordered by bucket (bit 31 = negated),
+ * offsets[nbuckets + 1] = start of every bucket in `sorted`, cap = reserved (pass 0).
+ * Returns the number of buckets whose sum (bucket + partial entries) differs from the XYZZ running sum.
+ * maxrun_out[7]: the run bound, then completed rounds, batched additions, doublings among them, division-free
+ * pairs + carried entries, abandoned rounds, mixed additions of the XYZZ finish.                                */
+B2Z_API int b2z_host_accum_affine(int group /*1|2*/, const uint32_t* points, const uint32_t* sorted,
+                                  const uint32_t* offsets, uint32_t nbuckets, uint32_t nseg, uint32_t cap,
+                                  uint32_t* maxrun_out);
 /* sum of n affine points (Montgomery limbs, 24 / 48 u32 each; neg[i] != 0 negates) with the
  * device's XYZZ mixed-addition code; out = affine sum, returns 1 if the sum is the identity. */
 B2Z_API int b2z_host_point_sum(int group /*1|2*/, const uint32_t* points, const uint8_t* neg, uint32_t n,

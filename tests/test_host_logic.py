@@ -84,6 +84,30 @@ def test_device_field_arithmetic_on_host(b2z, field, p, n):
     assert _val(out) == pow(a, -1, p) * R % p
 
 
+def test_division_step_inversion_on_host(b2z):
+    """csrc/inv_gcd.cuh against pow(a, -1, q): random, lazy (>= q), tiny, huge and power-of-two inputs; 0 -> 0."""
+    L = b2z._ffi.lib()
+    q, n = O.Q_MOD, 12
+    R = 1 << 384
+    rnd = random.Random(7)
+    cases = [1, 2, 3, q - 1, q - 2, (q - 1) // 2, (q + 1) // 2, 1 << 380, (1 << 380) + 1, R % q, pow(R, -1, q)]
+    cases += [1 << k for k in range(1, 380, 13)] + [rnd.randrange(1, q) for _ in range(1500)]
+    out = np.zeros(n, dtype=np.uint32)
+    worst = 0
+    for a in cases:
+        for lazy in (0, q):                      # the canonical value and its lazy twin a + q
+            if a + lazy >= 2 * q:
+                continue
+            batches = L.b2z_host_fq_inv_gcd(_arr32(a + lazy, n).ctypes.data, out.ctypes.data)
+            assert 0 < batches < 40, (hex(a), batches)
+            worst = max(worst, batches)
+            # input is x = a (taken as a Montgomery value a' R); output must be a'^-1 R = R^2 / x
+            assert _val(out) == pow(a, -1, q) * R * R % q, hex(a)
+    assert worst <= 37                            # (49 * 382 + 57) / 17 = 1104 division steps at most
+    assert L.b2z_host_fq_inv_gcd(_arr32(0, n).ctypes.data, out.ctypes.data) == 0 and _val(out) == 0
+    assert L.b2z_host_fq_inv_gcd(_arr32(q, n).ctypes.data, out.ctypes.data) == 0 and _val(out) == 0
+
+
 @pytest.mark.parametrize("group", [1, 2])
 def test_device_point_arithmetic_on_host(b2z, group):
     L = b2z._ffi.lib()
@@ -242,3 +266,55 @@ def test_uploaded_handles_are_bound_to_their_context_and_shard(b2z):
     with pytest.raises(ValueError):
         cm.upload(ctx_b)
     pk._handle = cm._handle = None          # nothing real to free
+
+
+def _accum_case(rnd, npoints, run_lengths, special):
+    """sorted references + bucket offsets with the given run lengths; `special` plants adversarial runs."""
+    sorted_refs, offsets = [], [0]
+    for b, R in enumerate(run_lengths):
+        kind = special.get(b)
+        if kind == "same":                       # one point over and over: a doubling at every tree level
+            refs = [5] * R
+        elif kind == "cancel":                   # P, -P, P, -P ...: identity markers travel up the tree
+            refs = [(7 | (0x80000000 if i & 1 else 0)) for i in range(R)]
+        elif kind == "mixed":                    # P, P, -P, -P, Q, ...
+            refs = ([9, 9, 9 | 0x80000000, 9 | 0x80000000] * (R // 4 + 1))[:R]
+        elif kind == "dup":                      # two equal points stored at different indices
+            refs = [0, 1] * (R // 2) + [0] * (R & 1)
+        else:
+            refs = [rnd.randrange(npoints) | (0x80000000 if rnd.random() < 0.4 else 0) for _ in range(R)]
+        sorted_refs += refs
+        offsets.append(len(sorted_refs))
+    return np.array(sorted_refs, dtype=np.uint32), np.array(offsets, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("group", [1, 2])
+def test_batched_affine_accumulation_on_host(b2z, group):
+    """csrc/accum_affine.cuh (tree rounds with a shared inversion + XYZZ finish) == the XYZZ running sum, bucket by
+    bucket, for ragged runs, runs cut by segment boundaries, doublings and cancellations."""
+    L = b2z._ffi.lib()
+    codec = b2z.codec
+    curve = O.G1 if group == 1 else O.G2
+    rnd = random.Random(40 + group)
+    npoints = 48 if group == 1 else 24
+    pts = [curve.mul(curve.gen, rnd.randrange(1, 1 << 24)) for _ in range(npoints)]
+    pts[1] = pts[0]
+    limbs = (codec.g1_to_limbs if group == 1 else codec.g2_to_limbs)(pts)[0]
+    big = 700 if group == 1 else 260
+    runs = [0, 1, 2, 3, 0, 5, 64, 33, big, 1, 1, 1, 130, 0, 0, 97, 40, 2, 31, 64, 50, 7]
+    special = {6: "same", 7: "cancel", 12: "mixed", 15: "dup", 18: "same", 19: "cancel"}
+    sorted_refs, offsets = _accum_case(rnd, npoints, runs, special)
+    nb = len(runs)
+    stats = np.zeros(7, dtype=np.uint32)
+    total = int(offsets[-1])
+    for nseg, cap in ((1, 0), (2, 0), (3, 0), (5, 0), (13, 0), (40, 0), (total // 8, 0)):
+        bad = L.b2z_host_accum_affine(group, limbs.ctypes.data, sorted_refs.ctypes.data, offsets.ctypes.data, nb, nseg,
+                                      cap, stats.ctypes.data)
+        assert bad == 0, (group, nseg, cap, bad)
+        _, rounds, batched, doublings, free, abandoned, finish = (int(v) for v in stats)
+        if nseg <= 5 and cap == 0:
+            # the tree really ran: most additions were batched, doublings and division-free pairs occurred
+            assert rounds >= 3 and batched > total // 2 and doublings > 0 and free > 0, tuple(stats)
+            assert batched + finish <= total
+        if nseg == total // 8:
+            assert rounds == 0 and finish > 0          # 8-reference segments go straight to the XYZZ finish

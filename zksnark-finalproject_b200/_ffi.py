@@ -83,6 +83,9 @@ SIGNATURES = {
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    "b2z_host_fq_inv_gcd": (ctypes.c_int, [vp, vp]),
+    "b2z_host_accum_affine": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32,
+                                              ctypes.c_uint32, vp]),
     "b2z_host_point_sum": (ctypes.c_int, [ctypes.c_int, vp, vp, ctypes.c_uint32, vp]),
     "b2z_host_msm_digits": (ctypes.c_uint32, [vp, ctypes.c_uint32, vp]),
     "b2z_host_msm_window_bits": (ctypes.c_uint32, [ctypes.c_uint64, ctypes.c_int]),

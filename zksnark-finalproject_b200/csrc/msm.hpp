@@ -64,6 +64,10 @@ struct MsmArena {
   DevBuf<uint32_t> hist, offsets, cursor, tile_sums, sorted;
   DevBuf<uint32_t> keys[2], state;
   DevBuf<uint8_t> buckets, parts[2], chunks[3], wsums;
+  // batched-affine accumulation (accum_affine.cuh): entry lists, their keys, prefix products, descriptors
+  DevBuf<uint8_t> aff_pts, aff_pref;
+  DevBuf<uint32_t> aff_keys;
+  DevBuf<uint4> aff_desc;
 };
 struct MsmScratch {
   MsmArena slot[8];
