@@ -504,22 +504,32 @@ class Bench:
         G1ACC = 3
         acc_ms = ms[G1ACC] / max(1, cnt[G1ACC])
         acc_adds = units[G1ACC] / max(1, cnt[G1ACC])
-        # algorithmic integer work: one XYZZ mixed addition = 10 Fq products = 10 x 600 IMAD-equivalents;
-        # peak = the measured 32-bit IMAD issue rate of this GPU (same run).  Algorithmic bytes: one 96 B affine base +
-        # one 4 B reference per addition.
+        # algorithmic integer work: one mixed addition = 10 Fq products = 10 x 600 IMAD-equivalents,
+        # whichever formula the kernel uses (the batched-affine kernel spends 6 products + a shared inversion on it, so
+        # its fraction says "additions per second against the XYZZ cost model", not pipe utilisation -- that is in
+        # profiles/*ncu*); peak = the measured 32-bit IMAD issue rate of this GPU (same run).  Algorithmic bytes: one
+        # 96 B affine base + one 4 B reference per addition.
         acc_imad = acc_adds * 6000.0
         acc_bytes = acc_adds * (96 + 4)
         t = acc_ms * 1e-3
+        AFF = 7
+        aff_launches, aff_adds = int(cnt[AFF]), float(units[AFF])
+        g1_aff_adds = min(aff_adds, float(units[G1ACC]))          # (G2 stays on the XYZZ kernel by default)
+        xyzz_adds = float(units[G1ACC]) - g1_aff_adds
+        # DRAM bytes per addition from the committed ncu --set full captures: 156 B (XYZZ kernel: bases + partial /
+        # bucket write-backs), 764 B (batched-affine kernel: bases read in both passes + the per-thread entry lists,
+        # prefix products and descriptors of every tree round)
+        traffic = (xyzz_adds * 156.0 + g1_aff_adds * 764.0) / max(1, cnt[G1ACC])
         roofline = {
-            "kernel": "G1 bucket accumulation (mixed additions of the sorted point references)",
+            "kernel": "G1 bucket accumulation (additions of the sorted point references; batched-affine kernel on "
+                      "%d of %d launches, XYZZ kernel on the rest)" % (min(aff_launches, int(cnt[G1ACC])), int(cnt[G1ACC])),
             "bound": "int", "achieved": acc_imad / t / 1e12 if t else None, "peak": imad.value / 1e12,
             "unit": "T IMAD-eq/s", "frac": (acc_imad / t / imad.value) if t and imad.value else None,
             "peak_source": "32-bit IMAD issue rate measured by b2z_measure_int_peak on this GPU in this run",
             "normaliser": "6000 IMAD-equivalents per G1 mixed addition (10 Fq products x 600; SURVEY.md 8(d), BASELINE.md)",
-            # dram bytes of one launch: constant from the committed ncu --set full capture (profiles/), scaled by adds
-            "traffic": acc_adds * 156.0,
-            "traffic_source": "constant 156 B per mixed addition from the ncu --set full capture under profiles/ "
-                              "(not re-measured per run)",
+            "traffic": traffic,
+            "traffic_source": "constants per addition from the ncu --set full captures under profiles/r02_ncu "
+                              "(156 B XYZZ kernel, 764 B batched-affine kernel; not re-measured per run)",
             "hbm": {"achieved": acc_bytes / t / 1e9 if t else None, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (acc_bytes / t / 1e9 / hbm_peak) if t else None, "peak_source": hbm_src,
                     "note": "not the binding roofline: the kernel is integer-pipe bound (SURVEY.md App. C)"},

@@ -236,7 +236,8 @@ B2Z_API b2z_status b2z_groth16_verify_with_processed_vk(const uint8_t* pvk, uint
  *   0 NTT pass kernels (units: field elements)   1 witness-map pointwise (elements)
  *   2 MSM digits + counting sort (scalars)       3 MSM bucket accumulation G1 (mixed adds)
  *   4 MSM bucket accumulation G2 (mixed adds)    5 MSM partial lists / bucket reduction / combine
- *   6 constraint-row evaluation (CSR SpMV of A, B, C against z)                          */
+ *   6 constraint-row evaluation (CSR SpMV of A, B, C against z)
+ *   7 the accumulation launches of 3 / 4 that took the batched-affine kernel (counted there too)   */
 #define B2Z_PHASE_COUNT 8
 B2Z_API b2z_status b2z_profile_enable(b2z_ctx* ctx, int on);
 B2Z_API b2z_status b2z_profile_read(b2z_ctx* ctx, double* ms, uint64_t* launches, uint64_t* units, int reset);

@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
 (timeout 900 python -m pytest tests/test_gpu_affine.py -x -q 2>&1 | tail -25) > gpurun_out/pytest_affine.log
 tail -3 gpurun_out/pytest_affine.log
-(timeout 600 python tools/ab_accum.py --size 64 --steps 4 --settings ${AB_SETTINGS:-xyzz,affine} > gpurun_out/ab_c5.jsonl 2> gpurun_out/ab_c5.err); echo ab rc $?
+(timeout 600 python tools/ab_accum.py --size 64 --steps ${AB_STEPS:-4} --settings ${AB_SETTINGS:-xyzz,affine} > gpurun_out/ab_c5.jsonl 2> gpurun_out/ab_c5.err); echo ab rc $?
 cat gpurun_out/ab_c5.jsonl | cut -c1-620; tail -3 gpurun_out/ab_c5.err
 if [ "${WITH_NCU:-1}" = "1" ]; then
 ncu --set full --clock-control none --import-source on -k regex:msm_accum_affine_kernel -s 4 -c 1 \

@@ -29,7 +29,7 @@ namespace b2z {
 namespace aff {
 
 constexpr uint32_t kNegBit = 0x80000000u;
-constexpr uint32_t kMinPairs = 24;
+constexpr uint32_t kMinPairsDefault = 24;
 
 // host emulation only: [0] completed rounds, [1] batched additions, [2] of which doublings, [3] division-free pairs
 // (identity marker / cancellation), [4] abandoned forward passes, [5] mixed additions of the XYZZ finish
@@ -113,6 +113,20 @@ B2Z_HD void st_xyzz(typename C::Xyzz* dst, const typename C::Xyzz& v) {
   st_el(&dst->zzz, v.zzz);
 }
 
+// The running sum of the XYZZ finish.  Default: the XYZZ point in registers (G1: 48 words).  The G2 kernel passes its
+// shared-memory sum instead (msm_impl.inc, RunningSum<G2>: 96 words do not fit beside an Fq2 product).
+template <class C>
+struct RegAcc {
+  typename C::Xyzz v;
+  B2Z_HD explicit RegAcc(uint32_t*) { v = C::identity(); }
+  B2Z_HD void reset() { v = C::identity(); }
+  // q = the entry at src, already loaded (and negated when `neg`); ro: src is read-only key data
+  B2Z_HD void madd(const typename C::Affine& q, const typename C::Affine* src, bool neg, bool) {
+    v = C::madd_inl_at(v, q, src, neg);
+  }
+  B2Z_HD void store(typename C::Xyzz* dst) const { st_xyzz<C>(dst, v); }
+};
+
 // Per-thread scratch (this thread's regions): two entry lists of as many entries as the segment is long (a round
 // never grows a list: every unit consumes at least one entry and emits one), one prefix product and one
 // descriptor per pair.
@@ -184,11 +198,12 @@ struct List {
 // One thread's segment [lo, hi) of the sorted references; `cur` = its first bucket (offsets[cur] <= lo <
 // offsets[cur + 1]).  Writes complete runs to bucket_out, cut runs to the two partial slots of `seg`.
 // active = false: a thread without a segment (it only takes part in the warp votes).
-template <class C>
+template <class C, class Acc = RegAcc<C>>
 B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sorted, const uint32_t* offsets,
                           bool active, uint32_t seg, uint32_t seg_len, uint32_t lo, uint32_t hi, uint32_t total,
                           uint32_t cur, typename C::Xyzz* bucket_out, uint32_t* part_keys,
-                          typename C::Xyzz* part_pts, uint32_t* maxrun, const Scratch<C>& S) {
+                          typename C::Xyzz* part_pts, uint32_t* maxrun, const Scratch<C>& S,
+                          uint32_t kMinPairs = kMinPairsDefault, uint32_t* acc_ctx = nullptr) {
   using F = typename C::Fld;
   using El = typename C::El;
   using Affine = typename C::Affine;
@@ -292,6 +307,32 @@ B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sort
     // first needed two products later)
     El inv = inverse(acc);
     const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+    if (sizeof(El) > sizeof(FqEl)) {
+      // Fq2: an element is 24 registers -- nothing is kept in flight; every operand is (re)loaded where it is
+      // consumed (the second reads hit L1) so that at most inv, lambda, x3 and one operand are live beside a product
+      uint4 de = npairs ? S.desc[npairs - 1] : none;
+      for (uint32_t k = npairs; k-- > 0;) {
+        const uint4 den = k ? S.desc[k - 1] : none;
+        El d = F::sub(L.x_of(de.y), L.x_of(de.x));
+        const bool dbl = F::is_zero(d);
+        if (dbl) d = F::dbl(L.y_of(de.x));
+        El lam = F::mul(inv, ld_el<false>(S.pref + k));       // 1 / d
+        inv = F::mul(inv, d);
+        if (dbl) {
+          B2Z_AFF_STAT(2, 1);
+          const El xx = F::sqr(L.x_of(de.x));
+          lam = F::mul(F::add(F::dbl(xx), xx), lam);
+        } else {
+          lam = F::mul(F::sub(L.y_of(de.y), L.y_of(de.x)), lam);
+        }
+        const El x1r = L.x_of(de.x);
+        const El x3 = F::sub(F::sub(F::sqr(lam), x1r), L.x_of(de.y));
+        st_el(&out[de.z].x, F::reduce(x3));
+        const El y3 = F::sub(F::mul(lam, F::sub(x1r, x3)), L.y_of(de.x));
+        st_el(&out[de.z].y, F::reduce(y3));
+        de = den;
+      }
+    } else {
     uint4 de = npairs ? S.desc[npairs - 1] : none;
     uint4 den = npairs > 1 ? S.desc[npairs - 2] : none;
     El x1b = L.x_of(de.x), x2b = L.x_of(de.y);
@@ -325,6 +366,7 @@ B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sort
       x2b = nx2;
       pf = npf;
     }
+    }
     B2Z_AFF_STAT(0, 1);
     B2Z_AFF_STAT(1, npairs);
     L.refs = false;
@@ -338,19 +380,19 @@ B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sort
   // ---- XYZZ finish over the current list
   bool wrote0 = false, wrote1 = false;
   uint32_t cur_key = L.key_at(0);
-  Xyzz acc = C::identity();
+  Acc acc(acc_ctx);
   auto flush = [&](uint32_t k) {
     const uint32_t b = offsets[k], e = offsets[k + 1];
     if (b < lo) {
       part_keys[2 * seg] = k;
-      st_xyzz<C>(part_pts + 2 * seg, acc);
+      acc.store(part_pts + 2 * seg);
       wrote0 = true;
     } else if (e > hi) {
       part_keys[2 * seg + 1] = k;
-      st_xyzz<C>(part_pts + 2 * seg + 1, acc);
+      acc.store(part_pts + 2 * seg + 1);
       wrote1 = true;
     } else {
-      st_xyzz<C>(bucket_out + k, acc);
+      acc.store(bucket_out + k);
     }
     // entries this bucket can have in the partial list: 2 per segment it touches
     if (b < lo || e > hi) raise_max(maxrun, 2 * ((umin(e, total) - 1) / seg_len - b / seg_len + 1));
@@ -359,7 +401,7 @@ B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sort
     const uint32_t key = L.key_at(i);
     if (key != cur_key) {
       flush(cur_key);
-      acc = C::identity();
+      acc.reset();
       cur_key = key;
     }
     const uint32_t h = L.handle(i, cnt);
@@ -368,7 +410,7 @@ B2Z_HD void accum_segment(const typename C::Affine* points, const uint32_t* sort
     q.y = L.y_of(h);
     if (all_zero(q.x) && all_zero(q.y)) continue;          // identity marker
     B2Z_AFF_STAT(5, 1);
-    acc = C::madd_inl_at(acc, q, L.ptr(h), L.negated(h));
+    acc.madd(q, L.ptr(h), L.negated(h), L.refs);
   }
   flush(cur_key);
   if (!wrote0) { part_keys[2 * seg] = first_key; st_xyzz<C>(part_pts + 2 * seg, C::identity()); }

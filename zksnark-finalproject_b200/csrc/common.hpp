@@ -88,6 +88,7 @@ enum Phase {
   PH_MSM_ACCUM_G2 = 4,  // bucket accumulation kernel, G2   units: mixed additions
   PH_MSM_REDUCE = 5,    // partial lists, bucket reduction, window combine
   PH_R1CS_EVAL = 6,     // constraint-row evaluation (CSR SpMV)
+  PH_MSM_ACCUM_AFFINE = 7,  // the accumulation launches (G1 or G2, also counted above) that took the batched-affine kernel
   PH_COUNT = 8
 };
 
