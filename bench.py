@@ -468,7 +468,8 @@ class Bench:
         units = (ctypes.c_uint64 * 8)()
         L.b2z_profile_read(ctx.handle, ms, cnt, units, 1)
         L.b2z_profile_enable(ctx.handle, 0)
-        names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
+        names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval",
+                 "msm_accum_affine"]
         base = min(a[i] for i in range(n)) if n else 0.0
         rows = [{"phase": names[ph[i]], "start_ms": a[i] - base, "stop_ms": b[i] - base}
                 for i in sorted(range(n), key=lambda i: a[i])]

@@ -30,7 +30,8 @@ for i in range(4):
 N = 4096
 ph = (ctypes.c_int * N)(); t0 = (ctypes.c_double * N)(); t1 = (ctypes.c_double * N)()
 n = ctx._lib.b2z_profile_spans(ctx.handle, N, ph, t0, t1)
-names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval"]
+names = ["ntt_pass", "wm_pointwise", "msm_sort", "msm_accum_g1", "msm_accum_g2", "msm_reduce", "r1cs_eval",
+         "msm_accum_affine"]
 base = min(t0[i] for i in range(n))
 for i in sorted(range(n), key=lambda i: t0[i]):
     print("%-14s %8.3f -> %8.3f  (%.3f ms)" % (names[ph[i]], t0[i] - base, t1[i] - base, t1[i] - t0[i]))
