@@ -518,9 +518,9 @@ class Bench:
         g1_aff_adds = min(aff_adds, float(units[G1ACC]))          # (G2 stays on the XYZZ kernel by default)
         xyzz_adds = float(units[G1ACC]) - g1_aff_adds
         # DRAM bytes per addition from the committed ncu --set full captures: 156 B (XYZZ kernel: bases + partial /
-        # bucket write-backs), 764 B (batched-affine kernel: bases read in both passes + the per-thread entry lists,
+        # bucket write-backs), 765 B (batched-affine kernel: bases read in both passes + the per-thread entry lists,
         # prefix products and descriptors of every tree round)
-        traffic = (xyzz_adds * 156.0 + g1_aff_adds * 764.0) / max(1, cnt[G1ACC])
+        traffic = (xyzz_adds * 156.0 + g1_aff_adds * 765.0) / max(1, cnt[G1ACC])
         roofline = {
             "kernel": "G1 bucket accumulation (additions of the sorted point references; batched-affine kernel on "
                       "%d of %d launches, XYZZ kernel on the rest)" % (min(aff_launches, int(cnt[G1ACC])), int(cnt[G1ACC])),
@@ -529,8 +529,9 @@ class Bench:
             "peak_source": "32-bit IMAD issue rate measured by b2z_measure_int_peak on this GPU in this run",
             "normaliser": "6000 IMAD-equivalents per G1 mixed addition (10 Fq products x 600; SURVEY.md 8(d), BASELINE.md)",
             "traffic": traffic,
-            "traffic_source": "constants per addition from the ncu --set full captures under profiles/r02_ncu "
-                              "(156 B XYZZ kernel, 764 B batched-affine kernel; not re-measured per run)",
+            "traffic_source": "constants per addition from the ncu --set full captures under profiles/r02_ncu and "
+                              "profiles/r02_ncu_final (dram__bytes_read + write per launch / additions: 156 B XYZZ "
+                              "kernel, 765 B batched-affine kernel; not re-measured per run)",
             "hbm": {"achieved": acc_bytes / t / 1e9 if t else None, "peak": hbm_peak, "unit": "GB/s",
                     "frac": (acc_bytes / t / 1e9 / hbm_peak) if t else None, "peak_source": hbm_src,
                     "note": "not the binding roofline: the kernel is integer-pipe bound (SURVEY.md App. C)"},
