@@ -443,12 +443,37 @@ class Bench:
                                    "sample": "%d full proof(s) of the same workload (%.2f s each); proof bytes equal "
                                              "the GPU's" % (self.args.cpu_steps, cdt)}
             del cpk
+        # ---- native witness generation for this workload (host only, outside every timed region; row f5)
+        if main and name in ("c2", "m8", "c5"):
+            res["witness_generation"] = self.witness_generation(name, z)
         key_bytes = self.key_bytes(n, m)
         res["key_bytes_resident_per_gpu"] = int(key_bytes // world)
         if pk is not None:
             pk.free()
         cm.free()
         return res
+
+    def witness_generation(self, name, z_builder):
+        """b2z_matrix_circuit_witness (csrc/witness.cu) on the host cores: the assignment the timed proofs consume,
+        regenerated natively and compared with the Python builder's.  Never fatal for the bench line."""
+        try:
+            W = self.pkg.witness
+            n = {"c2": 16, "m8": 8, "c5": 64}[name]
+            ones = [[1] * n for _ in range(n)]
+            params = W._default_params()
+            _, a = W._fr_matrix(ones)
+            out = self.np.empty_like(z_builder)
+            best = None
+            for _ in range(5):
+                t0 = time.perf_counter()
+                W.matrix_circuit_witness(a, a, params, threads=0, out=out)
+                dt = (time.perf_counter() - t0) * 1e3
+                best = dt if best is None else min(best, dt)
+            return {"ms": best, "threads": os.cpu_count(), "variables": int(out.shape[0]),
+                    "equals_python_builder": bool(self.np.array_equal(out, z_builder)),
+                    "call": "b2z_matrix_circuit_witness (host, std::thread; best of 5)"}
+        except Exception as e:                                                   # reported, not raised
+            return {"error": repr(e)}
 
     def dump_timeline(self, step, tag):
         """Development aid (B2Z_TIMELINE=dir): CUDA-event spans of ONE proof on this rank, relative to the first."""
@@ -607,6 +632,7 @@ def main():
             "cpu_baseline": res.get("cpu_baseline"), "phase_spans": res["phase_spans"],
             "collective": res["collective"], "replicas": res["replicas"],
             "key_bytes_resident_per_gpu": res.get("key_bytes_resident_per_gpu"), "proof_sha": res["proof_sha"],
+            "witness_generation": res.get("witness_generation"),
             "extra": extra,
         }
         emit(line)

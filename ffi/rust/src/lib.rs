@@ -82,6 +82,15 @@ pub mod sys {
         pub fn b2z_groth16_prepare_verifying_key(vk: *const b2z_vk_desc, pvk_out: *mut u8, capacity: u64, pvk_len: *mut u64) -> i32;
         pub fn b2z_groth16_verify_with_processed_vk(pvk: *const u8, pvk_len: u64, public_inputs: *const u64, num_inputs: u64,
                                                     proof: *const u8, valid: *mut i32) -> i32;
+        // host-side witness helpers (no ctx): Poseidon digest with the caller's PoseidonConfig, modpow tables
+        pub fn b2z_poseidon_hash(params: *const b2z_poseidon_desc, elems: *const u64, count: u64, digest_out: *mut u64) -> i32;
+        pub fn b2z_modpow_witnesses(base: u64, modulus: u64, exponent: u64, num_bits: u32, mod_vals: *mut u64,
+                                    mod_pow_vals: *mut u64, bits: *mut u8, result: *mut u64) -> i32;
+    }
+    #[repr(C)]
+    pub struct b2z_poseidon_desc {
+        pub full_rounds: u32, pub partial_rounds: u32, pub alpha: u64, pub width: u32, pub rate: u32, pub capacity: u32,
+        pub ark: *const u64, pub mds: *const u64,
     }
 }
 use sys::*;
@@ -323,6 +332,22 @@ pub fn ntt_in_place(ctx: &Context, data: &mut [Fr], inverse: bool, coset: Option
 
 // ---------------------------------------------------------------------------------------------- verifier (host only)
 /// `prepare_verifying_key(&vk)` + `serialize_compressed`: the bytes `encode_pvk` base64-encodes (io.rs:62-68).
+/// `hasher()` of the reference (matrix_proof_of_work/hasher.rs:17-27) on the host cores of the GPU box, with the
+/// caller's own `PoseidonConfig` (hashing_utils.rs: `poseidon_parameters_for_test`): absorb everything, squeeze one.
+pub fn poseidon_hash(cfg: &ark_crypto_primitives::sponge::poseidon::PoseidonConfig<Fr>, elems: &[Fr]) -> Result<Fr, SynthesisError> {
+    let ark: Vec<u64> = cfg.ark.iter().flat_map(|row| row.iter().flat_map(|x| x.0 .0)).collect();
+    let mds: Vec<u64> = cfg.mds.iter().flat_map(|row| row.iter().flat_map(|x| x.0 .0)).collect();
+    let d = b2z_poseidon_desc {
+        full_rounds: cfg.full_rounds as u32, partial_rounds: cfg.partial_rounds as u32, alpha: cfg.alpha,
+        width: (cfg.rate + cfg.capacity) as u32, rate: cfg.rate as u32, capacity: cfg.capacity as u32,
+        ark: ark.as_ptr(), mds: mds.as_ptr(),
+    };
+    let mut out = [0u64; 4];
+    let st = unsafe { b2z_poseidon_hash(&d, pack_fr(elems).as_ptr(), elems.len() as u64, out.as_mut_ptr()) };
+    if st != B2Z_OK { return Err(SynthesisError::AssignmentMissing); }
+    Ok(ark_ff::Fp(BigInt(out), core::marker::PhantomData))
+}
+
 pub fn prepared_vk_bytes(vk: &VerifyingKey<Bls12_381>) -> Result<Vec<u8>, SynthesisError> {
     let one = |p: &G1Affine| pack_g1(std::slice::from_ref(p)).0;
     let one2 = |p: &G2Affine| pack_g2(std::slice::from_ref(p)).0;

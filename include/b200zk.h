@@ -230,6 +230,55 @@ B2Z_API b2z_status b2z_groth16_verify_with_processed_vk(const uint8_t* pvk, uint
                                                         const uint64_t* public_inputs, uint64_t num_inputs,
                                                         const uint8_t proof[192], int32_t* valid);
 
+/* ---- witness generation on the host, multithreaded (no GPU, no ctx) ---------------------
+ * Once a proof takes tens of milliseconds the assignment itself is the next bottleneck.  The reference computes
+ * witnesses during synthesis (ark-r1cs-std), next to two native helpers restated here: hasher() -- the Poseidon sponge
+ * digest of a flattened matrix, absorb everything / squeeze one element
+ * (src/arkworks/matrix_proof_of_work/hasher.rs:17-27) -- and mod_pow_generate_witnesses()
+ * (src/arkworks/prime_snark/utils/modulo.rs:31-89).  The Poseidon parameters are ARGUMENTS (a Rust caller passes its
+ * PoseidonConfig: full_rounds, partial_rounds, alpha, ark, mds, rate, capacity -- hashing_utils.rs:701-715); the
+ * library carries no table.  All field elements: 4 x u64 Montgomery limbs, canonical (< r), else B2Z_EINVAL.       */
+typedef struct b2z_poseidon_desc {
+  uint32_t full_rounds;     /* even: half before and half after the partial rounds (8 in the reference)            */
+  uint32_t partial_rounds;  /* S-box on state[0] only (29)                                                          */
+  uint64_t alpha;           /* S-box exponent (17): left-to-right square-and-multiply, one witness per product      */
+  uint32_t width;           /* rate + capacity, 2 .. 8 (3)                                                          */
+  uint32_t rate;            /* (2)                                                                                  */
+  uint32_t capacity;        /* (1): rate slots sit AFTER the capacity slots in the state                            */
+  const uint64_t* ark;      /* (full_rounds + partial_rounds) x width round constants                               */
+  const uint64_t* mds;      /* width x width, row-major                                                             */
+} b2z_poseidon_desc;
+/* PoseidonSponge::new(params).absorb(elems).squeeze_native_field_elements(1)[0] */
+B2Z_API b2z_status b2z_poseidon_hash(const b2z_poseidon_desc* params, const uint64_t* elems, uint64_t count,
+                                     uint64_t digest_out[4]);
+/* Full assignment of the matrix-multiplication circuit for n x n inputs a, b (row-major)
+ * (matrix_proof_of_work/constraints.rs:78-128: witnesses A, B; C = A B with one product witness per scalar product
+ * and a zero-initialised sum witness per entry; public digests of A, B, C), in the variable order of this
+ * repository's circuit builder (zksnark-finalproject_b200/circuits.py: matrix_circuit):
+ *   [1, digest(A), digest(B), digest(C) | A | B | S-box witnesses of digest(A) | of digest(B) | n^2 zeros |
+ *    per (i, j): sum witness (0), a_i0 b_0j .. a_i,n-1 b_n-1,j | S-box witnesses of digest(C)]
+ * z_out: b2z_matrix_circuit_num_variables(params, n) elements, ready for b2z_groth16_prove_r1cs; B2Z_ESIZE when
+ * z_capacity (in elements) is smaller.  threads: 0 = all hardware threads.  The digests of A and B are independent
+ * sequential chains (one thread each) beside the n^3 products (the other threads); the digest of C follows.     */
+B2Z_API uint64_t b2z_matrix_circuit_num_variables(const b2z_poseidon_desc* params, uint32_t n);
+B2Z_API b2z_status b2z_matrix_circuit_witness(const b2z_poseidon_desc* params, uint32_t n, const uint64_t* a,
+                                              const uint64_t* b, uint32_t threads, uint64_t* z_out,
+                                              uint64_t z_capacity);
+/* Assignment of the Fibonacci circuit (src/arkworks/constraints/fibbonaci.rs:22-48): [1, a, b, F(num_steps) | 0],
+ * the result computed in Fr.                                                                                     */
+B2Z_API b2z_status b2z_fibonacci_witness(const uint64_t a[4], const uint64_t b[4], uint64_t num_steps,
+                                         uint64_t z_out[20]);
+/* mod_pow_generate_witnesses(base, div, exp) for base, modulus < 2^63 and num_bits table rows (the reference
+ * hard-codes 382): mod_pow_vals[i] = the i-th squaring of the chain power <- power^2 mod modulus, mod_vals[i] = the
+ * running product after exponent bit i (least significant first; rows past the exponent's length repeat the result
+ * with quotient 0), each row = (value lo, value hi, quotient lo, quotient hi, remainder) with value BEFORE the
+ * reduction; bits[i] = exponent bit i; *result = base^exponent mod modulus.  exponent must fit num_bits.
+ * (Where the reference's BigUint subtraction `cur_pow - 1` would panic -- cur_pow = 0 -- this returns the
+ * arithmetic value.)                                                                                            */
+B2Z_API b2z_status b2z_modpow_witnesses(uint64_t base, uint64_t modulus, uint64_t exponent, uint32_t num_bits,
+                                        uint64_t* mod_vals /* num_bits x 5 */, uint64_t* mod_pow_vals /* num_bits x 5 */,
+                                        uint8_t* bits /* num_bits */, uint64_t* result);
+
 /* ---- measurement hooks ----------------------------------------------------------------
  * Phase timers use CUDA events recorded on the stream each kernel is launched on.
  * Phases (index into the arrays of b2z_profile_read, length B2Z_PHASE_COUNT):

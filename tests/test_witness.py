@@ -1,0 +1,220 @@
+"""Native, multithreaded witness generation (csrc/witness.cu; include/b200zk.h row f5) against independent Python
+restatements: the symbolic circuit builders (big-int arithmetic), a plain Python Poseidon sponge with arkworks'
+PoseidonSponge structure, and mod_pow_generate_witnesses restated on Python integers
+(/root/reference/src/arkworks/matrix_proof_of_work/hasher.rs:17-27, constraints.rs:78-128,
+prime_snark/utils/modulo.rs:31-89, constraints/fibbonaci.rs:22-48).  Host only: no GPU needed."""
+import importlib
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bls12_381 as O
+
+R = O.R_MOD
+
+
+@pytest.fixture(scope="module")
+def W(b2z):
+    return b2z.witness
+
+
+@pytest.fixture(scope="module")
+def circuits():
+    return importlib.import_module("zksnark-finalproject_b200.circuits")
+
+
+@pytest.fixture(scope="module")
+def fast():
+    return importlib.import_module("zksnark-finalproject_b200.circuits_fast")
+
+
+# ---- independent Python sponge (PoseidonSponge::absorb / squeeze_native_field_elements(1))
+def _py_permute(p, state):
+    half = p.full_rounds // 2
+    for r in range(p.full_rounds + p.partial_rounds):
+        state = [(s + k) % R for s, k in zip(state, p.ark[r])]
+        if r < half or r >= half + p.partial_rounds:
+            state = [pow(s, p.alpha, R) for s in state]
+        else:
+            state[0] = pow(state[0], p.alpha, R)
+        state = [sum(p.mds[i][j] * state[j] for j in range(p.width)) % R for i in range(p.width)]
+    return state
+
+
+def _py_hash(p, elems):
+    state = [0] * p.width
+    pos = 0
+    for e in elems:
+        if pos == p.rate:
+            state = _py_permute(p, state)
+            pos = 0
+        state[p.capacity + pos] = (state[p.capacity + pos] + e) % R
+        pos += 1
+    return _py_permute(p, state)[p.capacity]
+
+
+def _params(W, rnd, full, partial, alpha, rate, capacity):
+    w = rate + capacity
+    return W.PoseidonParams(full, partial, alpha, [[rnd.randrange(R) for _ in range(w)] for _ in range(full + partial)],
+                            [[rnd.randrange(R) for _ in range(w)] for _ in range(w)], rate, capacity)
+
+
+@pytest.mark.parametrize("full,partial,alpha,rate,capacity", [(8, 29, 17, 2, 1), (8, 31, 5, 2, 1), (4, 3, 5, 3, 1),
+                                                              (2, 0, 3, 1, 1), (8, 5, 257, 4, 2), (6, 7, 7, 5, 3)])
+def test_poseidon_hash_against_python_sponge(W, full, partial, alpha, rate, capacity):
+    rnd = random.Random(alpha * 1000 + rate)
+    p = _params(W, rnd, full, partial, alpha, rate, capacity)
+    for count in (0, 1, rate - 1, rate, rate + 1, 2 * rate, 2 * rate + 1, 37):
+        elems = [rnd.randrange(R) for _ in range(count)]
+        assert W.poseidon_hash(elems, p) == _py_hash(p, elems), count
+    edge = [0, 1, R - 1, R - 2, 2 ** 64, 2 ** 255 % R]
+    assert W.poseidon_hash(edge, p) == _py_hash(p, edge)
+
+
+def test_poseidon_hash_equals_the_circuit_builders_digest(W, circuits):
+    ps = circuits.PoseidonShape()
+    rnd = random.Random(11)
+    for count in (1, 2, 3, 8, 9):
+        elems = [rnd.randrange(R) for _ in range(count)]
+        cs = circuits.ConstraintSystem()
+        want = cs.value(ps.hash(cs, [cs.new_witness(v) for v in elems]))
+        assert W.poseidon_hash(elems) == want
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_matrix_witness_equals_symbolic_builder_and_satisfies(W, b2z, circuits, n):
+    rnd = random.Random(n)
+    a = [[rnd.randrange(1 << 64) for _ in range(n)] for _ in range(n)]
+    b = [[rnd.randrange(1 << 64) for _ in range(n)] for _ in range(n)]
+    inst = circuits.matrix_circuit(a, b)
+    want = b2z.codec.fr_to_mont_limbs(inst.z)
+    assert W.matrix_circuit_num_variables(n) == inst.num_variables == len(inst.z)
+    for threads in (1, 2, 3, 4, 7, 0):
+        got = W.matrix_circuit_witness(a, b, threads=threads)
+        assert np.array_equal(got, want), threads
+    # and the native assignment satisfies the builder's constraint system
+    inst.z = b2z.codec.fr_from_mont_limbs(W.matrix_circuit_witness(a, b))
+    assert inst.is_satisfied()
+    inst.z[len(inst.z) // 2] = (inst.z[len(inst.z) // 2] + 1) % R
+    assert not inst.is_satisfied()
+
+
+@pytest.mark.parametrize("n,entries", [(8, "ones"), (16, "ones"), (16, "u64"), (12, "field")])
+def test_matrix_witness_equals_vectorised_builder(W, b2z, fast, n, entries):
+    """The reference's bench posts all-ones matrices (bench/matrix.py:10-11); its tests use u64 entries
+    (constraints.rs:326-330); full-size field elements exercise the reduction paths."""
+    rnd = random.Random(n)
+    gen = {"ones": lambda: 1, "u64": lambda: rnd.randrange(1 << 64), "field": lambda: rnd.randrange(R)}[entries]
+    a = [[gen() for _ in range(n)] for _ in range(n)]
+    b = [[gen() for _ in range(n)] for _ in range(n)]
+    cm, z = fast.matrix_circuit_fast(a, b)
+    want = b2z.codec.fr_to_mont_limbs(z)
+    for threads in (1, 3, 6, 0):
+        out = np.full(want.shape, 0xA5A5A5A5A5A5A5A5, dtype=np.uint64)       # every element must be written
+        got = W.matrix_circuit_witness(a, b, threads=threads, out=out)
+        assert got is out and np.array_equal(got, want), threads
+    # limb-array inputs (what a caller that already holds Fr elements passes)
+    la = b2z.codec.fr_to_mont_limbs([v for row in a for v in row])
+    lb = b2z.codec.fr_to_mont_limbs([v for row in b for v in row])
+    assert np.array_equal(W.matrix_circuit_witness(la, lb), want)
+
+
+def test_matrix_witness_with_other_parameters(W):
+    """Layout with another S-box / sponge geometry: x^5 (3 witnesses per S-box), rate 3."""
+    rnd = random.Random(99)
+    p = _params(W, rnd, 4, 5, 5, 3, 1)
+    n = 3
+    a = [[rnd.randrange(R) for _ in range(n)] for _ in range(n)]
+    b = [[rnd.randrange(R) for _ in range(n)] for _ in range(n)]
+    z = W.matrix_circuit_witness(a, b, p)
+    N, T, pv = n * n, 3, (4 * 4 + 5) * 3
+    assert z.shape[0] == 4 + 2 * N + 2 * T * pv + N + N * (1 + n) + T * pv == W.matrix_circuit_num_variables(n, p)
+    codec = importlib.import_module("zksnark-finalproject_b200.codec")
+    v = codec.fr_from_mont_limbs(z)
+    flat = lambda m: [x for row in m for x in row]
+    c = [sum(a[i][k] * b[k][j] for k in range(n)) % R for i in range(n) for j in range(n)]
+    assert v[0] == 1 and v[4:4 + N] == flat(a) and v[4 + N:4 + 2 * N] == flat(b)
+    assert v[1:4] == [_py_hash(p, flat(a)), _py_hash(p, flat(b)), _py_hash(p, c)]
+    w_mm = 4 + 2 * N + 2 * T * pv + N
+    assert v[w_mm - N:w_mm] == [0] * N
+    for i in range(n):
+        for j in range(n):
+            cell = v[w_mm + (i * n + j) * (1 + n):w_mm + (i * n + j + 1) * (1 + n)]
+            assert cell == [0] + [a[i][k] * b[k][j] % R for k in range(n)]
+    # first S-box of the digest of A: state = (0, a00, a01, a02) + ark[0], then x^2, x^4, x^5 of state[0]
+    x = p.ark[0][0] % R
+    assert v[4 + 2 * N:4 + 2 * N + 3] == [x * x % R, pow(x, 4, R), pow(x, 5, R)]
+
+
+def test_fibonacci_witness(W, b2z, circuits):
+    for a, b, steps in ((0, 1, 10), (0, 1, 1000), (3, 4, 0), (R - 1, R - 2, 5), (7, 11, 1)):
+        inst = circuits.fibonacci_circuit(a, b, steps)
+        assert np.array_equal(W.fibonacci_witness(a, b, steps), b2z.codec.fr_to_mont_limbs(inst.z)), (a, b, steps)
+
+
+def _py_modpow_witnesses(base, div, exp, num_bits):
+    """mod_pow_generate_witnesses on Python integers (modulo.rs:31-89), table length num_bits instead of 382."""
+    vals = lambda num: (num, num // div, num % div)
+    power, mod_pow_vals = base, []
+    for _ in range(num_bits):
+        power = power * power
+        mod_pow_vals.append(vals(power))
+        power %= div
+    cur, res, bits, v = base, 1, [0] * num_bits, []
+    counter = 0
+    while exp > 0:
+        elem = exp & 1
+        bits[counter] = elem
+        res *= (cur - 1) * elem + 1
+        v.append(vals(res))
+        if res > div:
+            res %= div
+        exp >>= 1
+        cur = cur * cur % div
+        counter += 1
+    v += [(res, 0, res)] * (num_bits - counter)
+    return {"mod_vals": v, "mod_pow_vals": mod_pow_vals, "bits": bits, "result": res}
+
+
+def test_modpow_witnesses(W):
+    rnd = random.Random(3)
+    cases = [(2, 1000003, 1000002, 20), (5, 7, 6, 20), (3, 2 ** 61 - 1, 2 ** 61 - 2, 64), (2, 3, 0, 8), (10, 11, 1, 1)]
+    for _ in range(40):
+        bits = rnd.choice([8, 20, 32, 63])
+        mod = rnd.randrange(2, 1 << rnd.choice([8, 20, 40, 62]))
+        cases.append((rnd.randrange(1, 1 << 62), mod, rnd.randrange(1 << bits), bits + rnd.randrange(3)))
+    for base, mod, exp, nb in cases:
+        got = W.modpow_witnesses(base, mod, exp, nb)
+        assert got == _py_modpow_witnesses(base, mod, exp, nb), (base, mod, exp, nb)
+        if got["result"] < mod:
+            assert got["result"] == pow(base, exp, mod)
+    # Fermat test of the reference's seed x = 5 -> candidate bases: a^(n-1) mod n == 1 for a prime n
+    assert W.modpow_witnesses(2, 1048583, 1048582, 21)["result"] == 1
+
+
+def test_witness_entry_points_reject_bad_arguments(W, b2z):
+    ffi = b2z._ffi
+    p = W._default_params()
+    with pytest.raises(ffi.B2zError) as e:                      # entry >= r is not a field element
+        W.matrix_circuit_witness(np.full((4, 4), 2 ** 64 - 1, dtype=np.uint64), np.zeros((4, 4), dtype=np.uint64), p)
+    assert e.value.status == ffi.B2Z_EINVAL
+    a = b2z.codec.fr_to_mont_limbs([1, 2, 3, 4])
+    d = p.desc()
+    L = ffi.lib()
+    m = W.matrix_circuit_num_variables(2, p)
+    small = np.zeros((m - 1, 4), dtype=np.uint64)
+    assert L.b2z_matrix_circuit_witness(d, 2, a.ctypes.data, a.ctypes.data, 0, small.ctypes.data, m - 1) == ffi.B2Z_ESIZE
+    assert L.b2z_matrix_circuit_witness(d, 0, a.ctypes.data, a.ctypes.data, 0, small.ctypes.data, m) == ffi.B2Z_EINVAL
+    assert L.b2z_matrix_circuit_witness(d, 2, None, a.ctypes.data, 0, small.ctypes.data, m) == ffi.B2Z_EINVAL
+    bad = W.PoseidonParams(8, 29, 17, p.ark, p.mds, 2, 1)
+    bad.full_rounds = 7                                           # odd number of full rounds
+    with pytest.raises(ffi.B2zError):
+        W.poseidon_hash([1, 2], bad)
+    assert W.matrix_circuit_num_variables(2, bad) == 0
+    with pytest.raises(ffi.B2zError):
+        W.modpow_witnesses(2, 1, 5, 8)                            # modulus < 2
+    with pytest.raises(ffi.B2zError):
+        W.modpow_witnesses(2, 7, 256, 8)                          # exponent does not fit num_bits
+    with pytest.raises(ffi.B2zError):
+        W.modpow_witnesses(2, 1 << 63, 3, 8)                      # modulus >= 2^63

@@ -32,6 +32,12 @@ class VkDesc(ctypes.Structure):
                 ("delta_g2", vp), ("gamma_abc_g1", vp), ("gamma_abc_inf", vp)]
 
 
+class PoseidonDesc(ctypes.Structure):
+    _fields_ = [("full_rounds", ctypes.c_uint32), ("partial_rounds", ctypes.c_uint32), ("alpha", ctypes.c_uint64),
+                ("width", ctypes.c_uint32), ("rate", ctypes.c_uint32), ("capacity", ctypes.c_uint32),
+                ("ark", vp), ("mds", vp)]
+
+
 # name -> (restype, argtypes); the test-suite checks this table against include/b200zk.h
 SIGNATURES = {
     "b2z_ctx_create": (ctypes.c_int32, [ctypes.c_int, ctypes.POINTER(vp)]),
@@ -82,6 +88,13 @@ SIGNATURES = {
     "b2z_dist_prove": (ctypes.c_int32, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),
+    "b2z_poseidon_hash": (ctypes.c_int32, [ctypes.POINTER(PoseidonDesc), vp, ctypes.c_uint64, vp]),
+    "b2z_matrix_circuit_num_variables": (ctypes.c_uint64, [ctypes.POINTER(PoseidonDesc), ctypes.c_uint32]),
+    "b2z_matrix_circuit_witness": (ctypes.c_int32, [ctypes.POINTER(PoseidonDesc), ctypes.c_uint32, vp, vp,
+                                                    ctypes.c_uint32, vp, ctypes.c_uint64]),
+    "b2z_fibonacci_witness": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, vp]),
+    "b2z_modpow_witnesses": (ctypes.c_int32, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
+                                              vp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     "b2z_host_fq_inv_gcd": (ctypes.c_int, [vp, vp]),
     "b2z_host_accum_affine": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32,

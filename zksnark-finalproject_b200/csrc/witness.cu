@@ -1,0 +1,390 @@
+// Witness generation on the host, multithreaded (include/b200zk.h): no GPU, no context.
+//
+// Once a proof takes tens of milliseconds, computing the assignment z is the next bottleneck (the Python builder of
+// this repository needs seconds for the 64x64 circuit).  The reference computes its witnesses during synthesis
+// (ark-r1cs-std gadgets), with two native helpers next to them whose behaviour is restated here:
+//   * hasher()  -- Poseidon sponge digest of a flattened matrix: absorb everything, squeeze one element
+//                  (src/arkworks/matrix_proof_of_work/hasher.rs:17-27; permutation structure as in the in-tree copy
+//                  hashing/hashing_utils.rs:737-802: ARK, S-box on the whole state in full rounds and on state[0] in
+//                  partial rounds, MDS; rounds full/2 | partial | full/2);
+//   * mod_pow_generate_witnesses() -- per-bit (value, quotient, remainder) tables of a right-to-left
+//                  square-and-multiply (src/arkworks/prime_snark/utils/modulo.rs:31-89).
+// The Poseidon parameters (round constants, MDS) are ARGUMENTS: the reference's table (hashing_utils.rs:15-715) is
+// data of the reference and is not carried here; a Rust caller passes its PoseidonConfig's `ark` / `mds`.
+//
+// b2z_matrix_circuit_witness produces the full assignment of the matrix-multiplication circuit
+// (matrix_proof_of_work/constraints.rs:78-128) in the variable order of this repository's circuit builder
+// (zksnark-finalproject_b200/circuits.py: matrix_circuit), as Montgomery limbs ready for b2z_groth16_prove_r1cs.
+// Threads: the digests of A and B are independent sequential chains (one thread each), the n^3 scalar products and
+// the n^2 sums are split over the remaining threads, the digest of C follows the sums.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <system_error>
+#include <thread>
+#include <vector>
+
+#include "../../include/b200zk.h"
+
+namespace {
+
+typedef unsigned __int128 u128;
+
+// ---- Fr, 4 x u64 Montgomery (R = 2^256), canonical representatives
+const uint64_t kMod[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+const uint64_t kInv = 0xfffffffeffffffffull;   // -r^-1 mod 2^64
+const uint64_t kR2[4] = {0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full, 0x0748d9d99f59ff11ull};
+
+struct Fr {
+  uint64_t l[4];
+};
+
+inline bool geq_mod(const uint64_t t[4]) {
+  for (int i = 3; i >= 0; i--)
+    if (t[i] != kMod[i]) return t[i] > kMod[i];
+  return true;
+}
+inline void sub_mod(uint64_t t[4]) {
+  uint64_t borrow = 0;
+  for (int i = 0; i < 4; i++) {
+    const u128 d = (u128)t[i] - kMod[i] - borrow;
+    t[i] = (uint64_t)d;
+    borrow = (uint64_t)(d >> 64) & 1;
+  }
+}
+inline Fr fr_add(const Fr& a, const Fr& b) {
+  Fr o;
+  uint64_t c = 0;
+  for (int i = 0; i < 4; i++) {
+    const u128 s = (u128)a.l[i] + b.l[i] + c;
+    o.l[i] = (uint64_t)s;
+    c = (uint64_t)(s >> 64);
+  }
+  if (c || geq_mod(o.l)) sub_mod(o.l);      // r < 2^255: a + b < 2^256, c is always 0; kept for clarity
+  return o;
+}
+// CIOS Montgomery product
+inline Fr fr_mul(const Fr& a, const Fr& b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) {
+      const u128 x = (u128)a.l[j] * b.l[i] + t[j] + c;
+      t[j] = (uint64_t)x;
+      c = (uint64_t)(x >> 64);
+    }
+    u128 x = (u128)t[4] + c;
+    t[4] = (uint64_t)x;
+    t[5] = (uint64_t)(x >> 64);
+    const uint64_t m = t[0] * kInv;
+    x = (u128)m * kMod[0] + t[0];
+    c = (uint64_t)(x >> 64);
+    for (int j = 1; j < 4; j++) {
+      x = (u128)m * kMod[j] + t[j] + c;
+      t[j - 1] = (uint64_t)x;
+      c = (uint64_t)(x >> 64);
+    }
+    x = (u128)t[4] + c;
+    t[3] = (uint64_t)x;
+    t[4] = t[5] + (uint64_t)(x >> 64);
+  }
+  Fr o;
+  std::memcpy(o.l, t, 32);
+  if (t[4] || geq_mod(o.l)) sub_mod(o.l);
+  return o;
+}
+inline Fr fr_zero() { return Fr{{0, 0, 0, 0}}; }
+inline Fr fr_from_u64(uint64_t v) {
+  Fr a{{v, 0, 0, 0}}, r2;
+  std::memcpy(r2.l, kR2, 32);
+  return fr_mul(a, r2);
+}
+inline bool fr_is_canonical(const uint64_t* l) { return !geq_mod(l); }
+inline Fr fr_load(const uint64_t* p) {
+  Fr a;
+  std::memcpy(a.l, p, 32);
+  return a;
+}
+inline void fr_store(uint64_t* p, const Fr& a) { std::memcpy(p, a.l, 32); }
+
+// ---- Poseidon
+constexpr uint32_t kMaxWidth = 8;
+
+struct Poseidon {
+  uint32_t full = 0, partial = 0, width = 0, rate = 0, capacity = 0;
+  uint64_t alpha = 0;
+  uint32_t sbox_vars = 0;            // witnesses one S-box allocates: squarings + multiplications of the power chain
+  std::vector<Fr> ark, mds;
+};
+
+// x^alpha by left-to-right square-and-multiply (FpVar::pow_by_constant); every squaring and every multiplication
+// is one witness; they are appended to *wit when it is not NULL.  alpha = 17: x^2, x^4, x^8, x^16, x^17.
+inline Fr sbox(const Poseidon& P, const Fr& x, Fr** wit) {
+  int top = 63;
+  while (!((P.alpha >> top) & 1)) top--;
+  Fr acc = x;
+  for (int b = top - 1; b >= 0; b--) {
+    acc = fr_mul(acc, acc);
+    if (wit) *(*wit)++ = acc;
+    if ((P.alpha >> b) & 1) {
+      acc = fr_mul(acc, x);
+      if (wit) *(*wit)++ = acc;
+    }
+  }
+  return acc;
+}
+
+uint32_t sbox_var_count(uint64_t alpha) {
+  int top = 63;
+  while (!((alpha >> top) & 1)) top--;
+  uint32_t n = 0;
+  for (int b = top - 1; b >= 0; b--) n += 1 + (uint32_t)((alpha >> b) & 1);
+  return n;
+}
+
+uint32_t perm_vars(const Poseidon& P) { return (P.full * P.width + P.partial) * P.sbox_vars; }
+
+void permute(const Poseidon& P, Fr* state, Fr* wit) {
+  const uint32_t half = P.full / 2, w = P.width;
+  Fr tmp[kMaxWidth];
+  Fr** wp = wit ? &wit : nullptr;
+  for (uint32_t r = 0; r < P.full + P.partial; r++) {
+    for (uint32_t i = 0; i < w; i++) state[i] = fr_add(state[i], P.ark[(size_t)r * w + i]);
+    const bool full_round = r < half || r >= half + P.partial;
+    const uint32_t ns = full_round ? w : 1;
+    for (uint32_t i = 0; i < ns; i++) state[i] = sbox(P, state[i], wp);
+    for (uint32_t i = 0; i < w; i++) {
+      Fr acc = fr_zero();
+      for (uint32_t j = 0; j < w; j++) acc = fr_add(acc, fr_mul(P.mds[(size_t)i * w + j], state[j]));
+      tmp[i] = acc;
+    }
+    for (uint32_t i = 0; i < w; i++) state[i] = tmp[i];
+  }
+}
+
+// sponge: absorb `count` elements (rate slots sit after the capacity; permute when the rate is full), one more
+// permutation, squeeze state[capacity].  wit (may be NULL): perm_vars() witnesses per permutation, in order.
+Fr sponge_digest(const Poseidon& P, const Fr* elems, size_t count, Fr* wit) {
+  Fr state[kMaxWidth];
+  for (uint32_t i = 0; i < P.width; i++) state[i] = fr_zero();
+  const uint32_t pv = perm_vars(P);
+  uint32_t pos = 0;
+  bool pending = false;
+  for (size_t e = 0; e < count; e++) {
+    if (pos == P.rate) {
+      permute(P, state, wit);
+      if (wit) wit += pv;
+      pos = 0;
+    }
+    state[P.capacity + pos] = fr_add(state[P.capacity + pos], elems[e]);
+    pos++;
+    pending = true;
+  }
+  // squeezing always permutes first (PoseidonSponge in absorbing mode), also after an empty absorb
+  (void)pending;
+  permute(P, state, wit);
+  return state[P.capacity];
+}
+
+size_t sponge_permutations(const Poseidon& P, size_t count) { return count ? (count + P.rate - 1) / P.rate : 1; }
+
+bool load_poseidon(const b2z_poseidon_desc* d, Poseidon* P) {
+  if (d == nullptr || d->ark == nullptr || d->mds == nullptr) return false;
+  if (d->width < 2 || d->width > kMaxWidth || d->rate == 0 || d->capacity == 0 || d->rate + d->capacity != d->width) return false;
+  if (d->alpha < 2 || (d->full_rounds & 1) || d->full_rounds + d->partial_rounds == 0 || d->full_rounds + d->partial_rounds > 4096)
+    return false;
+  P->full = d->full_rounds; P->partial = d->partial_rounds; P->width = d->width; P->rate = d->rate;
+  P->capacity = d->capacity; P->alpha = d->alpha; P->sbox_vars = sbox_var_count(d->alpha);
+  const size_t na = (size_t)(P->full + P->partial) * P->width, nm = (size_t)P->width * P->width;
+  P->ark.resize(na);
+  P->mds.resize(nm);
+  for (size_t i = 0; i < na; i++) {
+    if (!fr_is_canonical(d->ark + 4 * i)) return false;
+    P->ark[i] = fr_load(d->ark + 4 * i);
+  }
+  for (size_t i = 0; i < nm; i++) {
+    if (!fr_is_canonical(d->mds + 4 * i)) return false;
+    P->mds[i] = fr_load(d->mds + 4 * i);
+  }
+  return true;
+}
+
+uint32_t pick_threads(uint32_t want) {
+  if (want == 0) {
+    want = std::thread::hardware_concurrency();
+    if (want == 0) want = 4;
+  }
+  return std::min<uint32_t>(want, 256);
+}
+
+struct MatrixLayout {
+  uint64_t N, T, pv, w_a, w_b, w_ha, w_hb, w_cph, w_mm, w_hc, num_vars;
+};
+MatrixLayout matrix_layout(const Poseidon& P, uint32_t n) {
+  MatrixLayout L;
+  L.N = (uint64_t)n * n;
+  L.T = sponge_permutations(P, L.N);
+  L.pv = perm_vars(P);
+  L.w_a = 4;                                   // instance: 1, digest(A), digest(B), digest(C)
+  L.w_b = L.w_a + L.N;
+  L.w_ha = L.w_b + L.N;                        // S-box witnesses of the digest of A ...
+  L.w_hb = L.w_ha + L.T * L.pv;                // ... of B
+  L.w_cph = L.w_hb + L.T * L.pv;               // n^2 placeholder witnesses for C (zero)
+  L.w_mm = L.w_cph + L.N;                      // per (i, j): the zero-initialised sum witness, then n products
+  L.w_hc = L.w_mm + L.N * (1 + (uint64_t)n);
+  L.num_vars = L.w_hc + L.T * L.pv;
+  return L;
+}
+
+}  // namespace
+
+extern "C" {
+
+b2z_status b2z_poseidon_hash(const b2z_poseidon_desc* params, const uint64_t* elems, uint64_t count, uint64_t digest_out[4]) {
+  if (digest_out == nullptr || (count && elems == nullptr)) return B2Z_EINVAL;
+  try {
+    Poseidon P;
+    if (!load_poseidon(params, &P)) return B2Z_EINVAL;
+    std::vector<Fr> in(count);
+    for (uint64_t i = 0; i < count; i++) {
+      if (!fr_is_canonical(elems + 4 * i)) return B2Z_EINVAL;
+      in[i] = fr_load(elems + 4 * i);
+    }
+    fr_store(digest_out, sponge_digest(P, in.data(), count, nullptr));
+    return B2Z_OK;
+  } catch (const std::bad_alloc&) {
+    return B2Z_ENOMEM;
+  }
+}
+
+uint64_t b2z_matrix_circuit_num_variables(const b2z_poseidon_desc* params, uint32_t n) {
+  Poseidon P;
+  if (n == 0 || !load_poseidon(params, &P)) return 0;
+  return matrix_layout(P, n).num_vars;
+}
+
+b2z_status b2z_matrix_circuit_witness(const b2z_poseidon_desc* params, uint32_t n, const uint64_t* a, const uint64_t* b,
+                                      uint32_t threads, uint64_t* z_out, uint64_t z_capacity) {
+  if (n == 0 || a == nullptr || b == nullptr || z_out == nullptr) return B2Z_EINVAL;
+  try {
+    Poseidon P;
+    if (!load_poseidon(params, &P)) return B2Z_EINVAL;
+    const MatrixLayout L = matrix_layout(P, n);
+    if (z_capacity < L.num_vars) return B2Z_ESIZE;
+    for (uint64_t i = 0; i < L.N; i++)
+      if (!fr_is_canonical(a + 4 * i) || !fr_is_canonical(b + 4 * i)) return B2Z_EINVAL;
+    Fr* z = reinterpret_cast<Fr*>(z_out);
+    static_assert(sizeof(Fr) == 32, "Fr is four packed limbs");
+    z[0] = fr_from_u64(1);
+    std::memcpy(z + L.w_a, a, L.N * 32);
+    std::memcpy(z + L.w_b, b, L.N * 32);
+    std::memset(z + L.w_cph, 0, L.N * 32);
+    std::vector<Fr> c(L.N);
+    const uint32_t nt = pick_threads(threads);
+    // phase 1: digests of A and B (one thread each) beside the products and sums (the other threads, rows i)
+    auto products = [&](uint32_t lo, uint32_t hi) {
+      for (uint32_t i = lo; i < hi; i++)
+        for (uint32_t j = 0; j < n; j++) {
+          Fr* cell = z + L.w_mm + ((uint64_t)i * n + j) * (1 + (uint64_t)n);
+          cell[0] = fr_zero();                                     // the sum starts as a zero WITNESS
+          Fr acc = fr_zero();
+          for (uint32_t k = 0; k < n; k++) {
+            const Fr p = fr_mul(z[L.w_a + (uint64_t)i * n + k], z[L.w_b + (uint64_t)k * n + j]);
+            cell[1 + k] = p;
+            acc = fr_add(acc, p);
+          }
+          c[(uint64_t)i * n + j] = acc;
+        }
+    };
+    auto digest_a = [&]() { z[1] = sponge_digest(P, z + L.w_a, L.N, z + L.w_ha); };
+    auto digest_b = [&]() { z[2] = sponge_digest(P, z + L.w_b, L.N, z + L.w_hb); };
+    if (nt <= 1) {
+      digest_a();
+      digest_b();
+      products(0, n);
+    } else {
+      std::vector<std::thread> pool;
+      pool.emplace_back(digest_a);
+      if (nt >= 3) pool.emplace_back(digest_b);
+      const uint32_t workers = nt >= 4 ? std::min<uint32_t>(nt - 2, n) : 1;
+      std::vector<std::thread> mm;
+      for (uint32_t t = 1; t < workers; t++)
+        mm.emplace_back(products, (uint32_t)((uint64_t)n * t / workers), (uint32_t)((uint64_t)n * (t + 1) / workers));
+      products(0, (uint32_t)((uint64_t)n / workers));
+      if (nt < 3) digest_b();
+      for (auto& t : mm) t.join();
+      // phase 2 can start as soon as the sums are there: the digest of C runs on this thread while A / B finish
+      z[3] = sponge_digest(P, c.data(), L.N, z + L.w_hc);
+      for (auto& t : pool) t.join();
+      return B2Z_OK;
+    }
+    z[3] = sponge_digest(P, c.data(), L.N, z + L.w_hc);
+    return B2Z_OK;
+  } catch (const std::bad_alloc&) {
+    return B2Z_ENOMEM;
+  } catch (const std::system_error&) {
+    return B2Z_ENOMEM;
+  }
+}
+
+b2z_status b2z_fibonacci_witness(const uint64_t a[4], const uint64_t b[4], uint64_t num_steps, uint64_t z_out[20]) {
+  if (a == nullptr || b == nullptr || z_out == nullptr) return B2Z_EINVAL;
+  if (!fr_is_canonical(a) || !fr_is_canonical(b)) return B2Z_EINVAL;
+  Fr f2 = fr_load(a), f1 = fr_load(b);
+  for (uint64_t i = 0; i < num_steps; i++) {
+    const Fr fi = fr_add(f1, f2);
+    f2 = f1;
+    f1 = fi;
+  }
+  Fr* z = reinterpret_cast<Fr*>(z_out);
+  z[0] = fr_from_u64(1);
+  z[1] = fr_load(a);
+  z[2] = fr_load(b);
+  z[3] = num_steps ? f1 : fr_zero();
+  z[4] = fr_zero();                       // the one allocated witness (fibbonaci.rs:30) keeps its initial value
+  return B2Z_OK;
+}
+
+b2z_status b2z_modpow_witnesses(uint64_t base, uint64_t modulus, uint64_t exponent, uint32_t num_bits, uint64_t* mod_vals,
+                                uint64_t* mod_pow_vals, uint8_t* bits, uint64_t* result) {
+  if (modulus < 2 || modulus >> 63 || base >> 63 || num_bits == 0 || num_bits > 4096 || mod_vals == nullptr ||
+      mod_pow_vals == nullptr || bits == nullptr || result == nullptr)
+    return B2Z_EINVAL;
+  if (num_bits < 64 && (exponent >> num_bits)) return B2Z_EINVAL;
+  auto put = [](uint64_t* row, u128 num, uint64_t div) {          // (num lo, num hi, q lo, q hi, remainder)
+    const u128 q = num / div;
+    row[0] = (uint64_t)num; row[1] = (uint64_t)(num >> 64);
+    row[2] = (uint64_t)q; row[3] = (uint64_t)(q >> 64);
+    row[4] = (uint64_t)(num % div);
+  };
+  std::memset(bits, 0, num_bits);
+  // the squaring chain: power <- power^2, recorded BEFORE the reduction
+  u128 power = base;
+  for (uint32_t i = 0; i < num_bits; i++) {
+    power = power * power;
+    put(mod_pow_vals + 5 * (size_t)i, power, modulus);
+    power %= modulus;
+  }
+  // the running result, bit by bit from the least significant one
+  u128 res = 1, cur = base;
+  uint64_t e = exponent;
+  uint32_t counter = 0;
+  while (e > 0) {
+    const uint64_t bit = e & 1;
+    bits[counter] = (uint8_t)bit;
+    res *= bit ? cur : (u128)1;
+    put(mod_vals + 5 * (size_t)counter, res, modulus);
+    if (res > modulus) res %= modulus;
+    e >>= 1;
+    cur = (cur * cur) % modulus;
+    counter++;
+  }
+  for (uint32_t i = counter; i < num_bits; i++) {                  // padding rows: (res, 0, res)
+    uint64_t* row = mod_vals + 5 * (size_t)i;
+    row[0] = (uint64_t)res; row[1] = (uint64_t)(res >> 64); row[2] = 0; row[3] = 0; row[4] = (uint64_t)res;
+  }
+  *result = (uint64_t)res;
+  return B2Z_OK;
+}
+
+}  // extern "C"
