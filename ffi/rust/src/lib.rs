@@ -84,8 +84,14 @@ pub mod sys {
                                                     proof: *const u8, valid: *mut i32) -> i32;
         // host-side witness helpers (no ctx): Poseidon digest with the caller's PoseidonConfig, modpow tables
         pub fn b2z_poseidon_hash(params: *const b2z_poseidon_desc, elems: *const u64, count: u64, digest_out: *mut u64) -> i32;
+        pub fn b2z_prime_search(x: *const u64, j_first: u64, j_last: u64, num_bits: u32, k_bases: u32, threads: u32,
+                                out: *mut b2z_prime_check, found: *mut i32) -> i32;
         pub fn b2z_modpow_witnesses(base: u64, modulus: u64, exponent: u64, num_bits: u32, mod_vals: *mut u64,
                                     mod_pow_vals: *mut u64, bits: *mut u8, result: *mut u64) -> i32;
+    }
+    #[repr(C)]
+    pub struct b2z_prime_check {
+        pub j: u64, pub digest: [u8; 32], pub is_prime: i32, pub quotient: [u64; 4], pub remainder: u64, pub a: [u64; 4],
     }
     #[repr(C)]
     pub struct b2z_poseidon_desc {

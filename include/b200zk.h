@@ -279,6 +279,28 @@ B2Z_API b2z_status b2z_modpow_witnesses(uint64_t base, uint64_t modulus, uint64_
                                         uint64_t* mod_vals /* num_bits x 5 */, uint64_t* mod_pow_vals /* num_bits x 5 */,
                                         uint8_t* bits /* num_bits */, uint64_t* result);
 
+/* The prime route's native search (src/arkworks/backend/prime_snark.rs:60-70): for j = j_first .. j_last,
+ * check_if_next_is_prime(x, j) (prime_snark/prime_circut.rs:165-195) until one succeeds --
+ *   a_j = SHA-256(le32(x + j));  candidate = a_j mod 2^num_bits (utils/constants.rs: NUM_BITS = 20), quotient = a_j >> num_bits;
+ *   a = Fr::from_le_bytes_mod_order(SHA-256(le32(x + j) || a_j || le64(j)));
+ *   fermat_test(a, candidate) (fermat_circut.rs:131-141): bases SHA-256(le32(a) || le32(jj)) mod candidate for
+ *   jj < k_bases (constants.rs: K = 3), "prime" when ANY base b satisfies b^(candidate-1) = 1 mod candidate.
+ * The j are spread over `threads` host threads (0 = all); the SMALLEST successful j is returned, i.e. the reference's
+ * loop exit.  *found = 0: none in the range, *out then describes j_last.  x: Fr, Montgomery limbs.  num_bits <= 62.
+ * candidate = 0 (where the reference's BigUint division panics) counts as not prime.                              */
+typedef struct b2z_prime_check {
+  uint64_t j;
+  uint8_t digest[32];      /* a_j, the bytes SHA-256 produced (IsPrimeStruct.0)                                   */
+  int32_t is_prime;        /* IsPrimeStruct.1                                                                     */
+  uint64_t quotient[4];    /* IsPrimeStruct.2.q, little-endian limbs                                              */
+  uint64_t remainder;      /* IsPrimeStruct.2.remainder: the candidate                                            */
+  uint64_t a[4];           /* IsPrimeStruct.3: canonical integer, little-endian limbs                             */
+} b2z_prime_check;
+B2Z_API b2z_status b2z_prime_search(const uint64_t x[4], uint64_t j_first, uint64_t j_last, uint32_t num_bits,
+                                    uint32_t k_bases, uint32_t threads, b2z_prime_check* out, int32_t* found);
+/* SHA-256 of a byte string (the `sha2` crate the native side of the prime route uses) */
+B2Z_API void b2z_sha256(const uint8_t* data, uint64_t len, uint8_t digest_out[32]);
+
 /* ---- measurement hooks ----------------------------------------------------------------
  * Phase timers use CUDA events recorded on the stream each kernel is launched on.
  * Phases (index into the arrays of b2z_profile_read, length B2Z_PHASE_COUNT):

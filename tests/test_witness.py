@@ -3,6 +3,7 @@ restatements: the symbolic circuit builders (big-int arithmetic), a plain Python
 PoseidonSponge structure, and mod_pow_generate_witnesses restated on Python integers
 (/root/reference/src/arkworks/matrix_proof_of_work/hasher.rs:17-27, constraints.rs:78-128,
 prime_snark/utils/modulo.rs:31-89, constraints/fibbonaci.rs:22-48).  Host only: no GPU needed."""
+import hashlib
 import importlib
 import random
 
@@ -218,3 +219,70 @@ def test_witness_entry_points_reject_bad_arguments(W, b2z):
         W.modpow_witnesses(2, 7, 256, 8)                          # exponent does not fit num_bits
     with pytest.raises(ffi.B2zError):
         W.modpow_witnesses(2, 1 << 63, 3, 8)                      # modulus >= 2^63
+
+
+# ---- the prime route's native side, restated with hashlib and Python integers
+def _py_check_if_next_is_prime(x, j, num_bits=20, k=3):
+    le32 = lambda v: (v % R).to_bytes(32, "little")
+    xb = le32(x + j)
+    a_j = hashlib.sha256(xb).digest()
+    num = int.from_bytes(a_j, "little")
+    q, p = num >> num_bits, num & ((1 << num_bits) - 1)
+    a = int.from_bytes(hashlib.sha256(xb + a_j + j.to_bytes(8, "little")).digest(), "little") % R
+    is_prime = False
+    if p:
+        for jj in range(k):
+            base = int.from_bytes(hashlib.sha256(le32(a) + le32(jj)).digest(), "little") % p
+            if pow(base, p - 1, p) == 1:
+                is_prime = True
+                break
+    return {"digest": a_j, "is_prime": is_prime, "quotient": q, "remainder": p, "a": a}
+
+
+def test_sha256_known_answers(W):
+    assert W.sha256(b"").hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    assert W.sha256(b"abc").hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert (W.sha256(b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq").hex()
+            == "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1")
+    rnd = random.Random(1)
+    for n in (1, 55, 56, 57, 63, 64, 65, 119, 120, 128, 1000):
+        data = bytes(rnd.randrange(256) for _ in range(n))
+        assert W.sha256(data) == hashlib.sha256(data).digest(), n
+
+
+@pytest.mark.parametrize("x", [5, 0, 123456789, 2 ** 64 - 1])          # x = 5: the reference's own test seed
+def test_prime_search_follows_the_reference_loop(W, x):
+    # every j on its own (single-j ranges), against the Python restatement
+    first = None
+    for j in range(0, 40):
+        want = _py_check_if_next_is_prime(x, j)
+        got = W.prime_search(x, j, j)
+        assert {k: got[k] for k in want} == want and got["j"] == j and got["found"] == want["is_prime"], j
+        if want["is_prime"] and first is None:
+            first = j
+    # the loop of prove_prime: first success in 0..=i, whatever the thread count
+    for threads in (1, 2, 3, 8, 0):
+        got = W.prime_search(x, 0, 39, threads=threads)
+        if first is None:
+            assert not got["found"] and got["j"] == 39
+        else:
+            assert got["found"] and got["j"] == first and got["is_prime"]
+            assert got["remainder"] == _py_check_if_next_is_prime(x, first)["remainder"]
+    if first is not None and first > 0:                            # a range that ends before the first hit
+        got = W.prime_search(x, 0, first - 1, threads=4)
+        assert not got["found"] and got["j"] == first - 1
+        assert got["digest"] == _py_check_if_next_is_prime(x, first - 1)["digest"]
+
+
+def test_prime_search_other_widths_and_bad_arguments(W, b2z):
+    rnd = random.Random(8)
+    for _ in range(20):
+        x, j, nb, k = rnd.randrange(R), rnd.randrange(1 << 40), rnd.choice([1, 8, 20, 31, 32, 33, 62]), rnd.choice([1, 3, 5])
+        want = _py_check_if_next_is_prime(x, j, nb, k)
+        got = W.prime_search(x, j, j, num_bits=nb, k_bases=k)
+        assert {kk: got[kk] for kk in want} == want, (x, j, nb, k)
+    for bad in (dict(num_bits=0), dict(num_bits=63), dict(k_bases=0)):
+        with pytest.raises(b2z._ffi.B2zError):
+            W.prime_search(5, 0, 3, **bad)
+    with pytest.raises(b2z._ffi.B2zError):
+        W.prime_search(5, 4, 3)

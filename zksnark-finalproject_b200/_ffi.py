@@ -38,6 +38,11 @@ class PoseidonDesc(ctypes.Structure):
                 ("ark", vp), ("mds", vp)]
 
 
+class PrimeCheck(ctypes.Structure):
+    _fields_ = [("j", ctypes.c_uint64), ("digest", ctypes.c_uint8 * 32), ("is_prime", ctypes.c_int32),
+                ("quotient", ctypes.c_uint64 * 4), ("remainder", ctypes.c_uint64), ("a", ctypes.c_uint64 * 4)]
+
+
 # name -> (restype, argtypes); the test-suite checks this table against include/b200zk.h
 SIGNATURES = {
     "b2z_ctx_create": (ctypes.c_int32, [ctypes.c_int, ctypes.POINTER(vp)]),
@@ -95,6 +100,9 @@ SIGNATURES = {
     "b2z_fibonacci_witness": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, vp]),
     "b2z_modpow_witnesses": (ctypes.c_int32, [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32,
                                               vp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "b2z_prime_search": (ctypes.c_int32, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_uint32, ctypes.POINTER(PrimeCheck), ctypes.POINTER(ctypes.c_int32)]),
+    "b2z_sha256": (None, [vp, ctypes.c_uint64, vp]),
     "b2z_host_field_op": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     "b2z_host_fq_inv_gcd": (ctypes.c_int, [vp, vp]),
     "b2z_host_accum_affine": (ctypes.c_int, [ctypes.c_int, vp, vp, vp, ctypes.c_uint32, ctypes.c_uint32,

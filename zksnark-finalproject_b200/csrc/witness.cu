@@ -388,3 +388,210 @@ b2z_status b2z_modpow_witnesses(uint64_t base, uint64_t modulus, uint64_t expone
 }
 
 }  // extern "C"
+
+// ---- SHA-256 (FIPS 180-4) and the prime route's native search -------------------------------------------------------
+namespace {
+
+const uint32_t kShaK[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+struct Sha256 {
+  uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+  uint8_t buf[64];
+  uint64_t len = 0;
+  void block(const uint8_t* p) {
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++)
+      w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+      const uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+      const uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+      const uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + kShaK[i] + w[i];
+      const uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  void update(const uint8_t* p, size_t n) {
+    while (n) {
+      const size_t fill = (size_t)(len & 63), take = std::min<size_t>(n, 64 - fill);
+      std::memcpy(buf + fill, p, take);
+      len += take; p += take; n -= take;
+      if (((len & 63) == 0)) block(buf);
+    }
+  }
+  void finalize(uint8_t out[32]) {
+    const uint64_t bits = len * 8;
+    const uint8_t one = 0x80, zero = 0;
+    update(&one, 1);
+    while ((len & 63) != 56) update(&zero, 1);
+    uint8_t lb[8];
+    for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+    update(lb, 8);
+    for (int i = 0; i < 8; i++) {
+      out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16);
+      out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i];
+    }
+  }
+};
+
+// canonical little-endian bytes of an Fr element given in Montgomery form (into_bigint().to_bytes_le())
+inline void fr_to_le_bytes(const Fr& mont, uint8_t out[32]) {
+  const Fr one{{1, 0, 0, 0}};
+  const Fr c = fr_mul(mont, one);                 // a R * 1 / R = a
+  std::memcpy(out, c.l, 32);                      // x86-64: limbs are little-endian already
+}
+// 256-bit little-endian integer (4 limbs) mod a 64-bit modulus
+inline uint64_t mod_u256(const uint64_t v[4], uint64_t m) {
+  u128 rem = 0;
+  for (int i = 3; i >= 0; i--) rem = ((rem << 64) | v[i]) % m;
+  return (uint64_t)rem;
+}
+inline uint64_t modpow_u64(uint64_t base, uint64_t e, uint64_t m) {
+  if (m == 1) return 0;
+  u128 res = 1, b = base % m;
+  while (e) {
+    if (e & 1) res = res * b % m;
+    b = b * b % m;
+    e >>= 1;
+  }
+  return (uint64_t)res;
+}
+
+struct PrimeCheck {
+  uint8_t digest[32];      // a_j = SHA-256(le32(x + j))
+  bool is_prime;
+  uint64_t q[4];           // a_j >> num_bits
+  uint64_t remainder;      // a_j mod 2^num_bits: the candidate
+  uint64_t a[4];           // Fr::from_le_bytes_mod_order(SHA-256(le32(x + j) || a_j || le64(j))), canonical
+};
+
+// check_if_next_is_prime(x, j) (prime_circut.rs:165-195) with fermat_test / generate_bases_native inlined
+PrimeCheck prime_check(const Fr& x_mont, uint64_t j, uint32_t num_bits, uint32_t k_bases) {
+  PrimeCheck R;
+  uint8_t xb[32];
+  fr_to_le_bytes(fr_add(x_mont, fr_from_u64(j)), xb);
+  Sha256 s1;
+  s1.update(xb, 32);
+  s1.finalize(R.digest);
+  uint64_t aj[4];
+  std::memcpy(aj, R.digest, 32);                  // BigUint::from_bytes_le
+  // a_j = q * 2^num_bits + remainder
+  const uint32_t ws = num_bits / 64, bs = num_bits % 64;
+  for (int i = 0; i < 4; i++) {
+    uint64_t lo = (i + ws < 4) ? aj[i + ws] : 0, hi = (i + ws + 1 < 4) ? aj[i + ws + 1] : 0;
+    R.q[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+  }
+  R.remainder = num_bits >= 64 ? aj[0] : aj[0] & ((1ull << num_bits) - 1);
+  // r = SHA-256(le32(x + j) || a_j || j as 8 little-endian bytes), reduced mod the scalar field
+  uint8_t jb[8], rb[32];
+  for (int i = 0; i < 8; i++) jb[i] = (uint8_t)(j >> (8 * i));
+  Sha256 s2;
+  s2.update(xb, 32);
+  s2.update(R.digest, 32);
+  s2.update(jb, 8);
+  s2.finalize(rb);
+  std::memcpy(R.a, rb, 32);
+  while (geq_mod(R.a)) sub_mod(R.a);              // 2^256 < 3 r: at most two subtractions
+  // fermat_test(a, p): bases SHA-256(le32(a) || le32(jj)) mod p; "prime" when ANY base passes (fermat_circut.rs:131-141)
+  const uint64_t p = R.remainder;
+  R.is_prime = false;
+  if (p == 0) return R;                           // the reference divides by zero here (BigUint panic)
+  uint8_t ab[32];
+  std::memcpy(ab, R.a, 32);
+  for (uint32_t jj = 0; jj < k_bases && !R.is_prime; jj++) {
+    uint8_t jjb[32] = {0}, d[32];
+    for (int i = 0; i < 4; i++) jjb[i] = (uint8_t)(jj >> (8 * i));
+    Sha256 s3;
+    s3.update(ab, 32);
+    s3.update(jjb, 32);
+    s3.finalize(d);
+    uint64_t v[4];
+    std::memcpy(v, d, 32);
+    const uint64_t base = mod_u256(v, p);
+    if (modpow_u64(base, p - 1, p) == 1) R.is_prime = true;
+  }
+  return R;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b2z_sha256(const uint8_t* data, uint64_t len, uint8_t digest_out[32]) {
+  Sha256 s;
+  if (len) s.update(data, (size_t)len);
+  s.finalize(digest_out);
+}
+
+b2z_status b2z_prime_search(const uint64_t x[4], uint64_t j_first, uint64_t j_last, uint32_t num_bits, uint32_t k_bases,
+                            uint32_t threads, b2z_prime_check* out, int32_t* found) {
+  if (x == nullptr || out == nullptr || found == nullptr || j_last < j_first || num_bits == 0 || num_bits > 62 ||
+      k_bases == 0 || k_bases > 64 || !fr_is_canonical(x))
+    return B2Z_EINVAL;
+  try {
+    const Fr xm = fr_load(x);
+    const uint64_t total = j_last - j_first + 1;
+    uint32_t nt = pick_threads(threads);
+    if ((uint64_t)nt > total) nt = (uint32_t)total;
+    // ranks take j = j_first + t, j_first + t + nt, ...: the smallest hit of all ranks is the reference's loop exit
+    std::vector<uint64_t> hit(nt, UINT64_MAX);
+    std::vector<PrimeCheck> res(nt);
+    std::vector<PrimeCheck> last(nt);
+    auto work = [&](uint32_t t) {
+      for (uint64_t off = t; off < total; off += nt) {
+        const uint64_t j = j_first + off;
+        bool stop = false;
+        for (uint32_t u = 0; u < nt; u++)
+          if (__atomic_load_n(&hit[u], __ATOMIC_RELAXED) < j) stop = true;      // somebody found a smaller j
+        if (stop) return;
+        PrimeCheck c = prime_check(xm, j, num_bits, k_bases);
+        if (j == j_last) last[t] = c;
+        if (c.is_prime) {
+          res[t] = c;
+          __atomic_store_n(&hit[t], j, __ATOMIC_RELAXED);
+          return;
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (uint32_t t = 1; t < nt; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    uint32_t best = nt;
+    for (uint32_t t = 0; t < nt; t++)
+      if (hit[t] != UINT64_MAX && (best == nt || hit[t] < hit[best])) best = t;
+    const PrimeCheck* c;
+    uint64_t j;
+    if (best != nt) {
+      c = &res[best]; j = hit[best]; *found = 1;
+    } else {                                       // none: report j_last, as the reference's loop leaves check_result
+      c = &last[(uint32_t)((total - 1) % nt)]; j = j_last; *found = 0;
+    }
+    out->j = j;
+    std::memcpy(out->digest, c->digest, 32);
+    out->is_prime = c->is_prime ? 1 : 0;
+    std::memcpy(out->quotient, c->q, 32);
+    out->remainder = c->remainder;
+    std::memcpy(out->a, c->a, 32);
+    return B2Z_OK;
+  } catch (const std::bad_alloc&) {
+    return B2Z_ENOMEM;
+  } catch (const std::system_error&) {
+    return B2Z_ENOMEM;
+  }
+}
+
+}  // extern "C"

@@ -6,6 +6,8 @@ no GPU.  Mirrors the reference's native helpers next to its gadgets --
                            (matrix_proof_of_work/constraints.rs:78-128), in the variable order of circuits.matrix_circuit
   fibonacci_witness        FibonacciCircuit (constraints/fibbonaci.rs:22-48)
   modpow_witnesses         mod_pow_generate_witnesses() (prime_snark/utils/modulo.rs:31-89)
+  prime_search             the prove_prime loop over check_if_next_is_prime (backend/prime_snark.rs:60-70,
+                           prime_snark/prime_circut.rs:165-195, fermat_circut.rs:131-141), spread over host threads
 
 The Poseidon parameters are arguments (PoseidonParams); nothing here carries the reference's constant table.
 """
@@ -130,3 +132,25 @@ def modpow_witnesses(base, modulus, exponent, num_bits):
                                            _ptr(bits), ctypes.byref(res)), "b2z_modpow_witnesses")
     rows = lambda t: [(int(r[0]) | (int(r[1]) << 64), int(r[2]) | (int(r[3]) << 64), int(r[4])) for r in t]
     return {"mod_vals": rows(mv), "mod_pow_vals": rows(pv), "bits": [int(x) for x in bits], "result": int(res.value)}
+
+
+def sha256(data):
+    """SHA-256 of a byte string through the library (the native side of the prime route hashes with the sha2 crate)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8).copy() if len(data) else np.zeros(0, np.uint8)
+    out = np.zeros(32, dtype=np.uint8)
+    _ffi.lib().b2z_sha256(_ptr(buf) if len(data) else None, len(data), _ptr(out))
+    return out.tobytes()
+
+
+def prime_search(x, j_first, j_last, num_bits=20, k_bases=3, threads=0):
+    """First j in [j_first, j_last] for which check_if_next_is_prime(Fr::from(x), j) succeeds.
+    -> dict(found, j, digest (32 bytes), is_prime, quotient, remainder (the candidate), a); found = False: the entry
+    describes j_last."""
+    xl = np.ascontiguousarray(codec.fr_to_mont_limbs([int(x)]))
+    out = _ffi.PrimeCheck()
+    found = ctypes.c_int32()
+    _check(_ffi.lib().b2z_prime_search(_ptr(xl), int(j_first), int(j_last), int(num_bits), int(k_bases), int(threads),
+                                       ctypes.byref(out), ctypes.byref(found)), "b2z_prime_search")
+    big = lambda limbs: sum(int(v) << (64 * i) for i, v in enumerate(limbs))
+    return {"found": bool(found.value), "j": int(out.j), "digest": bytes(out.digest), "is_prime": bool(out.is_prime),
+            "quotient": big(out.quotient), "remainder": int(out.remainder), "a": big(out.a)}
