@@ -1,18 +1,24 @@
 """Native, multithreaded witness generation (csrc/witness.cu; include/b200zk.h row f5) against independent Python
-restatements: the symbolic circuit builders (big-int arithmetic), a plain Python Poseidon sponge with arkworks'
-PoseidonSponge structure, and mod_pow_generate_witnesses restated on Python integers
+restatements: oracle/witness.py (Poseidon sponge with arkworks' PoseidonSponge structure, mod_pow_generate_witnesses,
+check_if_next_is_prime on hashlib + Python integers), the symbolic circuit builders (big-int arithmetic) and the
+committed vectors tests/golden/witness_vectors.json
 (/root/reference/src/arkworks/matrix_proof_of_work/hasher.rs:17-27, constraints.rs:78-128,
-prime_snark/utils/modulo.rs:31-89, constraints/fibbonaci.rs:22-48).  Host only: no GPU needed."""
+prime_snark/utils/modulo.rs:31-89, prime_snark/prime_circut.rs:149-195, constraints/fibbonaci.rs:22-48).
+Host only: no GPU needed."""
 import hashlib
 import importlib
+import json
+import os
 import random
 
 import numpy as np
 import pytest
 
 from oracle import bls12_381 as O
+from oracle import witness as OW
 
 R = O.R_MOD
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -30,29 +36,10 @@ def fast():
     return importlib.import_module("zksnark-finalproject_b200.circuits_fast")
 
 
-# ---- independent Python sponge (PoseidonSponge::absorb / squeeze_native_field_elements(1))
-def _py_permute(p, state):
-    half = p.full_rounds // 2
-    for r in range(p.full_rounds + p.partial_rounds):
-        state = [(s + k) % R for s, k in zip(state, p.ark[r])]
-        if r < half or r >= half + p.partial_rounds:
-            state = [pow(s, p.alpha, R) for s in state]
-        else:
-            state[0] = pow(state[0], p.alpha, R)
-        state = [sum(p.mds[i][j] * state[j] for j in range(p.width)) % R for i in range(p.width)]
-    return state
-
-
 def _py_hash(p, elems):
-    state = [0] * p.width
-    pos = 0
-    for e in elems:
-        if pos == p.rate:
-            state = _py_permute(p, state)
-            pos = 0
-        state[p.capacity + pos] = (state[p.capacity + pos] + e) % R
-        pos += 1
-    return _py_permute(p, state)[p.capacity]
+    """oracle/witness.py on the parameters of a witness.PoseidonParams"""
+    return OW.poseidon_hash(OW.PoseidonConfig(p.full_rounds, p.partial_rounds, p.alpha, p.ark, p.mds, p.rate, p.capacity),
+                            elems)
 
 
 def _params(W, rnd, full, partial, alpha, rate, capacity):
@@ -154,28 +141,7 @@ def test_fibonacci_witness(W, b2z, circuits):
         assert np.array_equal(W.fibonacci_witness(a, b, steps), b2z.codec.fr_to_mont_limbs(inst.z)), (a, b, steps)
 
 
-def _py_modpow_witnesses(base, div, exp, num_bits):
-    """mod_pow_generate_witnesses on Python integers (modulo.rs:31-89), table length num_bits instead of 382."""
-    vals = lambda num: (num, num // div, num % div)
-    power, mod_pow_vals = base, []
-    for _ in range(num_bits):
-        power = power * power
-        mod_pow_vals.append(vals(power))
-        power %= div
-    cur, res, bits, v = base, 1, [0] * num_bits, []
-    counter = 0
-    while exp > 0:
-        elem = exp & 1
-        bits[counter] = elem
-        res *= (cur - 1) * elem + 1
-        v.append(vals(res))
-        if res > div:
-            res %= div
-        exp >>= 1
-        cur = cur * cur % div
-        counter += 1
-    v += [(res, 0, res)] * (num_bits - counter)
-    return {"mod_vals": v, "mod_pow_vals": mod_pow_vals, "bits": bits, "result": res}
+_py_modpow_witnesses = OW.mod_pow_generate_witnesses
 
 
 def test_modpow_witnesses(W):
@@ -221,22 +187,7 @@ def test_witness_entry_points_reject_bad_arguments(W, b2z):
         W.modpow_witnesses(2, 1 << 63, 3, 8)                      # modulus >= 2^63
 
 
-# ---- the prime route's native side, restated with hashlib and Python integers
-def _py_check_if_next_is_prime(x, j, num_bits=20, k=3):
-    le32 = lambda v: (v % R).to_bytes(32, "little")
-    xb = le32(x + j)
-    a_j = hashlib.sha256(xb).digest()
-    num = int.from_bytes(a_j, "little")
-    q, p = num >> num_bits, num & ((1 << num_bits) - 1)
-    a = int.from_bytes(hashlib.sha256(xb + a_j + j.to_bytes(8, "little")).digest(), "little") % R
-    is_prime = False
-    if p:
-        for jj in range(k):
-            base = int.from_bytes(hashlib.sha256(le32(a) + le32(jj)).digest(), "little") % p
-            if pow(base, p - 1, p) == 1:
-                is_prime = True
-                break
-    return {"digest": a_j, "is_prime": is_prime, "quotient": q, "remainder": p, "a": a}
+_py_check_if_next_is_prime = OW.check_if_next_is_prime
 
 
 def test_sha256_known_answers(W):
@@ -286,3 +237,21 @@ def test_prime_search_other_widths_and_bad_arguments(W, b2z):
             W.prime_search(5, 0, 3, **bad)
     with pytest.raises(b2z._ffi.B2zError):
         W.prime_search(5, 4, 3)
+
+
+def test_golden_witness_vectors(W):
+    """tests/golden/witness_vectors.json (made by make_witness_golden.py from oracle/witness.py alone)."""
+    with open(os.path.join(ROOT, "tests", "golden", "witness_vectors.json")) as f:
+        g = json.load(f)
+    assert g["producer"] == "oracle"
+    for c in g["prime_search"]:
+        got = W.prime_search(c["x"], 0, c["i"])
+        assert got["found"] and got["j"] == c["j"] and got["digest"].hex() == c["digest"]
+        assert got["remainder"] == c["remainder"] and got["quotient"] == int(c["quotient"], 16) and got["a"] == int(c["a"], 16)
+    for c in g["modpow"]:
+        got = W.modpow_witnesses(c["base"], c["modulus"], c["exponent"], c["num_bits"])
+        assert got["result"] == c["result"] and got["bits"] == c["bits"]
+        assert got["mod_vals"] == [tuple(int(v, 16) for v in row) for row in c["mod_vals"]]
+        assert got["mod_pow_vals"] == [tuple(int(v, 16) for v in row) for row in c["mod_pow_vals"]]
+    for c in g["poseidon"]:
+        assert W.poseidon_hash([int(e, 16) for e in c["elems"]]) == int(c["digest"], 16)
