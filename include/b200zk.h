@@ -230,6 +230,28 @@ B2Z_API b2z_status b2z_groth16_verify_with_processed_vk(const uint8_t* pvk, uint
                                                         const uint64_t* public_inputs, uint64_t num_inputs,
                                                         const uint8_t proof[192], int32_t* valid);
 
+/* ---- key-generation scalars on the host, multithreaded (row f3; no GPU, no ctx) ---------------------------------
+ * ark_groth16's generate_parameters_with_qap (Groth16::setup, matrix_proof.rs:128-131) = O(n) scalar preparation + fixed-
+ * base multiplications.  The multiplications are b2z_fixed_base_mul_g1/g2 (and b2z_spmv_fr for the QAP evaluation at
+ * tau) on the GPU; these are the scalar part: exact element-wise vector operations over Fr, split over host threads
+ * (threads = 0: all).  Elements are 4 x u64 Montgomery limbs; scalars (tau, base, scale, a, b, c) must be canonical (< r),
+ * else B2Z_EINVAL; vector elements are reduced on load; outputs are canonical; `out` may alias an input.
+ *   b2z_fr_lagrange_at   out[i] = L_i(tau) = Z(tau)/n * w^i / (tau - w^i), i < count <= n = 2^log_n, w the domain's
+ *                        generator (LibsnarkReduction::instance_map_with_evaluation's evaluate_all_lagrange_coefficients);
+ *                        B2Z_EINVAL when tau lies in the domain
+ *   b2z_fr_geometric     out[i] = scale * base^i  (the h query's  tau^i Z(tau) / delta)
+ *   b2z_fr_lincomb3      out[i] = a x[i] + b y[i] + c z[i]; a NULL vector drops its term  (beta A_i + alpha B_i + C_i, and
+ *                        the gamma^-1 / delta^-1 scalings)
+ *   b2z_fr_into_bigint   Montgomery -> canonical integer limbs (what b2z_fixed_base_mul_* and b2z_msm_* take)          */
+B2Z_API b2z_status b2z_fr_lagrange_at(uint32_t log_n, const uint64_t tau[4], uint64_t count, uint32_t threads,
+                                      uint64_t* out);
+B2Z_API b2z_status b2z_fr_geometric(const uint64_t base[4], const uint64_t scale[4], uint64_t count, uint32_t threads,
+                                    uint64_t* out);
+B2Z_API b2z_status b2z_fr_lincomb3(uint64_t count, const uint64_t a[4], const uint64_t* x, const uint64_t b[4],
+                                   const uint64_t* y, const uint64_t c[4], const uint64_t* z, uint32_t threads,
+                                   uint64_t* out);
+B2Z_API b2z_status b2z_fr_into_bigint(uint64_t count, const uint64_t* in, uint32_t threads, uint64_t* out);
+
 /* ---- witness generation on the host, multithreaded (no GPU, no ctx) ---------------------
  * Once a proof takes tens of milliseconds the assignment itself is the next bottleneck.  The reference computes
  * witnesses during synthesis (ark-r1cs-std), next to two native helpers restated here: hasher() -- the Poseidon sponge

@@ -93,6 +93,10 @@ SIGNATURES = {
     "b2z_dist_prove": (ctypes.c_int32, [vp, vp, vp, ctypes.c_int, vp, vp, vp]),
     "b2z_host_register": (ctypes.c_int32, [vp, vp, ctypes.c_uint64]),
     "b2z_host_unregister": (ctypes.c_int32, [vp, vp]),
+    "b2z_fr_lagrange_at": (ctypes.c_int32, [ctypes.c_uint32, vp, ctypes.c_uint64, ctypes.c_uint32, vp]),
+    "b2z_fr_geometric": (ctypes.c_int32, [vp, vp, ctypes.c_uint64, ctypes.c_uint32, vp]),
+    "b2z_fr_lincomb3": (ctypes.c_int32, [ctypes.c_uint64, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp]),
+    "b2z_fr_into_bigint": (ctypes.c_int32, [ctypes.c_uint64, vp, ctypes.c_uint32, vp]),
     "b2z_poseidon_hash": (ctypes.c_int32, [ctypes.POINTER(PoseidonDesc), vp, ctypes.c_uint64, vp]),
     "b2z_matrix_circuit_num_variables": (ctypes.c_uint64, [ctypes.POINTER(PoseidonDesc), ctypes.c_uint32]),
     "b2z_matrix_circuit_witness": (ctypes.c_int32, [ctypes.POINTER(PoseidonDesc), ctypes.c_uint32, vp, vp,

@@ -25,87 +25,13 @@
 #include <vector>
 
 #include "../../include/b200zk.h"
+#include "host_fr.hpp"
+
+using namespace b2z::hostfr;
 
 namespace {
 
-typedef unsigned __int128 u128;
-
-// ---- Fr, 4 x u64 Montgomery (R = 2^256), canonical representatives
-const uint64_t kMod[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
-const uint64_t kInv = 0xfffffffeffffffffull;   // -r^-1 mod 2^64
-const uint64_t kR2[4] = {0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full, 0x0748d9d99f59ff11ull};
-
-struct Fr {
-  uint64_t l[4];
-};
-
-inline bool geq_mod(const uint64_t t[4]) {
-  for (int i = 3; i >= 0; i--)
-    if (t[i] != kMod[i]) return t[i] > kMod[i];
-  return true;
-}
-inline void sub_mod(uint64_t t[4]) {
-  uint64_t borrow = 0;
-  for (int i = 0; i < 4; i++) {
-    const u128 d = (u128)t[i] - kMod[i] - borrow;
-    t[i] = (uint64_t)d;
-    borrow = (uint64_t)(d >> 64) & 1;
-  }
-}
-inline Fr fr_add(const Fr& a, const Fr& b) {
-  Fr o;
-  uint64_t c = 0;
-  for (int i = 0; i < 4; i++) {
-    const u128 s = (u128)a.l[i] + b.l[i] + c;
-    o.l[i] = (uint64_t)s;
-    c = (uint64_t)(s >> 64);
-  }
-  if (c || geq_mod(o.l)) sub_mod(o.l);      // r < 2^255: a + b < 2^256, c is always 0; kept for clarity
-  return o;
-}
-// CIOS Montgomery product
-inline Fr fr_mul(const Fr& a, const Fr& b) {
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; i++) {
-    uint64_t c = 0;
-    for (int j = 0; j < 4; j++) {
-      const u128 x = (u128)a.l[j] * b.l[i] + t[j] + c;
-      t[j] = (uint64_t)x;
-      c = (uint64_t)(x >> 64);
-    }
-    u128 x = (u128)t[4] + c;
-    t[4] = (uint64_t)x;
-    t[5] = (uint64_t)(x >> 64);
-    const uint64_t m = t[0] * kInv;
-    x = (u128)m * kMod[0] + t[0];
-    c = (uint64_t)(x >> 64);
-    for (int j = 1; j < 4; j++) {
-      x = (u128)m * kMod[j] + t[j] + c;
-      t[j - 1] = (uint64_t)x;
-      c = (uint64_t)(x >> 64);
-    }
-    x = (u128)t[4] + c;
-    t[3] = (uint64_t)x;
-    t[4] = t[5] + (uint64_t)(x >> 64);
-  }
-  Fr o;
-  std::memcpy(o.l, t, 32);
-  if (t[4] || geq_mod(o.l)) sub_mod(o.l);
-  return o;
-}
-inline Fr fr_zero() { return Fr{{0, 0, 0, 0}}; }
-inline Fr fr_from_u64(uint64_t v) {
-  Fr a{{v, 0, 0, 0}}, r2;
-  std::memcpy(r2.l, kR2, 32);
-  return fr_mul(a, r2);
-}
-inline bool fr_is_canonical(const uint64_t* l) { return !geq_mod(l); }
-inline Fr fr_load(const uint64_t* p) {
-  Fr a;
-  std::memcpy(a.l, p, 32);
-  return a;
-}
-inline void fr_store(uint64_t* p, const Fr& a) { std::memcpy(p, a.l, 32); }
+// Fr arithmetic: host_fr.hpp
 
 // ---- Poseidon
 constexpr uint32_t kMaxWidth = 8;

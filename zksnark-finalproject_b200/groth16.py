@@ -20,6 +20,7 @@ Nothing here computes on the CPU: every method forwards to CUDA through the C
 ABI and raises if the library or the GPU is missing.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -562,6 +563,9 @@ class Groth16:
         zt = (pow(tau, n, R_MOD) - 1) % R_MOD
         if zt == 0:
             raise ValueError("tau lies in the evaluation domain")
+        if cm is not None and not os.environ.get("B2Z_SETUP_PYTHON"):
+            return Groth16._generate_parameters_native(ctx, cm, num_constraints, l, m, n, log_n, zt,
+                                                       alpha, beta, gamma, delta, tau)
         # Lagrange coefficients L_i(tau) = Z(tau)/n * w^i / (tau - w^i)
         ws, cur = [], 1
         for _ in range(n):
@@ -621,6 +625,81 @@ class Groth16:
         pk = ProvingKey(m, l, n, g1(at), g1(bt), g2(bt), g1(hs), g1([x * dinv_ % R_MOD for x in abc[l:]]),
                         singles1[0], singles1[1], singles1[2], singles2[0], singles2[2])
         vk = VerifyingKey(singles1[0], singles2[0], singles2[1], singles2[2], g1([x * ginv % R_MOD for x in abc[:l]]))
+        return pk, vk
+
+    @staticmethod
+    def _generate_parameters_native(ctx, cm, num_constraints, l, m, n, log_n, zt, alpha, beta, gamma, delta, tau):
+        """generate_parameters_with_qap for CSR matrices with the O(n) scalar preparation done by the library's
+        multithreaded host helpers (b2z_fr_lagrange_at / _geometric / _lincomb3 / _into_bigint, csrc/setup_host.cu)
+        instead of Python integers: the arrays handed to b2z_spmv_fr and b2z_fixed_base_mul_* are bit-identical to the
+        ones the integer path builds (tests/test_setup_host.py), a 2^22 key takes seconds instead of ~20 s."""
+        L = ctx._lib
+        mont = lambda v: np.ascontiguousarray(codec.fr_to_mont_limbs([v]))
+        one = mont(1)
+
+        def lincomb(count, terms):
+            """terms: up to three (coefficient int, (count, 4) array); -> new (count, 4) array"""
+            out = np.empty((count, 4), dtype=np.uint64)
+            args, keep = [], []
+            for k in range(3):
+                if k < len(terms):
+                    cf = mont(terms[k][0])
+                    arr = np.ascontiguousarray(terms[k][1])
+                    keep += [cf, arr]
+                    args += [_ptr(cf), _ptr(arr)]
+                else:
+                    args += [None, None]
+            if count:
+                ctx.check(L.b2z_fr_lincomb3(count, *args, 0, _ptr(out)))
+            return out
+
+        def bigint(arr):
+            out = np.empty_like(arr)
+            if arr.shape[0]:
+                ctx.check(L.b2z_fr_into_bigint(arr.shape[0], _ptr(arr), 0, _ptr(out)))
+            return out
+
+        nl = num_constraints + l
+        lag = np.empty((nl, 4), dtype=np.uint64)
+        tau_l = mont(tau)
+        ctx.check(L.b2z_fr_lagrange_at(log_n, _ptr(tau_l), nl, 0, _ptr(lag)))
+        lag_limbs = np.ascontiguousarray(lag[:num_constraints])
+
+        def qap(mat):
+            rp, cols, cf = mat
+            nnz = cols.shape[0]
+            rows_of = np.repeat(np.arange(num_constraints, dtype=np.uint32), np.diff(rp.astype(np.int64)))
+            order = np.argsort(cols, kind="stable")
+            t_rp = np.zeros(m + 1, dtype=np.uint64)
+            np.add.at(t_rp, cols.astype(np.int64) + 1, 1)
+            t_rp = np.cumsum(t_rp).astype(np.uint64)
+            t_cols = np.ascontiguousarray(rows_of[order])
+            t_cf = np.ascontiguousarray(cf[order])
+            y = np.zeros((m, 4), dtype=np.uint64)
+            ctx.check(L.b2z_spmv_fr(ctx.handle, m, num_constraints, _ptr(t_rp), _ptr(t_cols), _ptr(t_cf),
+                                    _ptr(lag_limbs), _ptr(y)))
+            assert nnz == int(t_rp[-1])
+            return y
+        at, bt, ct = qap(cm.a), qap(cm.b), qap(cm.c)
+        # the instance rows a[num_constraints + j] = z[j] of the witness map: A_j(tau) += L_{nc + j}(tau)
+        at[:l] = lincomb(l, [(1, at[:l]), (1, lag[num_constraints:nl])])
+        abc = lincomb(m, [(beta, at), (alpha, bt), (1, ct)])
+        ginv, dinv_ = pow(gamma, -1, R_MOD), pow(delta, -1, R_MOD)
+        hs = np.empty((n - 1, 4), dtype=np.uint64)
+        if n > 1:
+            scale = mont(zt * dinv_ % R_MOD)
+            ctx.check(L.b2z_fr_geometric(_ptr(tau_l), _ptr(scale), n - 1, 0, _ptr(hs)))
+        l_sc = lincomb(m - l, [(dinv_, abc[l:])])
+        g_sc = lincomb(l, [(ginv, abc[:l])])
+        g1 = lambda arr: FixedBase.msm_g1(ctx, arr) if arr.shape[0] else (np.zeros((0, 12), np.uint64), None)
+        g2 = lambda arr: FixedBase.msm_g2(ctx, arr) if arr.shape[0] else (np.zeros((0, 24), np.uint64), None)
+        big = codec.fr_to_bigint_limbs
+        singles1, _ = FixedBase.msm_g1(ctx, big([alpha, beta, delta]))
+        singles2, _ = FixedBase.msm_g2(ctx, big([beta, gamma, delta]))
+        at_b, bt_b = bigint(at), bigint(bt)
+        pk = ProvingKey(m, l, n, g1(at_b), g1(bt_b), g2(bt_b), g1(bigint(hs)), g1(bigint(l_sc)),
+                        singles1[0], singles1[1], singles1[2], singles2[0], singles2[2])
+        vk = VerifyingKey(singles1[0], singles2[0], singles2[1], singles2[2], g1(bigint(g_sc)))
         return pk, vk
 
     @staticmethod
