@@ -564,8 +564,14 @@ class Groth16:
         if zt == 0:
             raise ValueError("tau lies in the evaluation domain")
         if cm is not None and not os.environ.get("B2Z_SETUP_PYTHON"):
-            return Groth16._generate_parameters_native(ctx, cm, num_constraints, l, m, n, log_n, zt,
-                                                       alpha, beta, gamma, delta, tau)
+            # scalar preparation by the library's multithreaded host helpers; the integer path below computes the very
+            # same arrays (tests/test_setup_host.py) and takes over if a helper reports an error
+            try:
+                return Groth16._generate_parameters_native(ctx, cm, num_constraints, l, m, n, log_n, zt,
+                                                           alpha, beta, gamma, delta, tau)
+            except _ffi.B2zError as e:
+                import sys
+                print("[b200zk] native key-generation scalars failed (%s); using the integer path" % (e,), file=sys.stderr)
         # Lagrange coefficients L_i(tau) = Z(tau)/n * w^i / (tau - w^i)
         ws, cur = [], 1
         for _ in range(n):
