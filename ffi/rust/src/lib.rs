@@ -82,6 +82,16 @@ pub mod sys {
         pub fn b2z_groth16_prepare_verifying_key(vk: *const b2z_vk_desc, pvk_out: *mut u8, capacity: u64, pvk_len: *mut u64) -> i32;
         pub fn b2z_groth16_verify_with_processed_vk(pvk: *const u8, pvk_len: u64, public_inputs: *const u64, num_inputs: u64,
                                                     proof: *const u8, valid: *mut i32) -> i32;
+        // key-generation scalars on the host cores (no ctx): see INTEGRATION.md section 7
+        pub fn b2z_fr_lagrange_at(log_n: u32, tau: *const u64, count: u64, threads: u32, out: *mut u64) -> i32;
+        pub fn b2z_fr_geometric(base: *const u64, scale: *const u64, count: u64, threads: u32, out: *mut u64) -> i32;
+        pub fn b2z_fr_lincomb3(count: u64, a: *const u64, x: *const u64, b: *const u64, y: *const u64, c: *const u64,
+                               z: *const u64, threads: u32, out: *mut u64) -> i32;
+        pub fn b2z_fr_into_bigint(count: u64, input: *const u64, threads: u32, out: *mut u64) -> i32;
+        pub fn b2z_spmv_fr(ctx: *mut b2z_ctx, nrows: u64, ncols: u64, row_ptr: *const u64, cols: *const u32,
+                           coeffs: *const u64, x: *const u64, y_out: *mut u64) -> i32;
+        pub fn b2z_fixed_base_mul_g1(ctx: *mut b2z_ctx, scalars: *const u64, n: u64, out_points: *mut u64, out_inf: *mut u8) -> i32;
+        pub fn b2z_fixed_base_mul_g2(ctx: *mut b2z_ctx, scalars: *const u64, n: u64, out_points: *mut u64, out_inf: *mut u8) -> i32;
         // host-side witness helpers (no ctx): Poseidon digest with the caller's PoseidonConfig, modpow tables
         pub fn b2z_poseidon_hash(params: *const b2z_poseidon_desc, elems: *const u64, count: u64, digest_out: *mut u64) -> i32;
         pub fn b2z_prime_search(x: *const u64, j_first: u64, j_last: u64, num_bits: u32, k_bases: u32, threads: u32,
